@@ -1,0 +1,175 @@
+/*
+ * kantts_b200.h -- C ABI of libkantts_b200.so, the sm_100a implementation of the
+ * KAN-TTS HiFi-GAN hot path (generator / discriminator convolutions, DWT pooling,
+ * mel-spectrogram loss).
+ *
+ * The reference (modelscope/KAN-TTS) has no FFI layer: the path sits behind Python
+ * nn.Modules that dispatch to ATen/cuDNN/cuFFT.  Each entry point below replaces the
+ * library dispatch of one reference call site (cited per function, paths relative to
+ * the KAN-TTS checkout).  Conventions:
+ *   - plain pointers and sizes only, all buffers caller-allocated DEVICE memory,
+ *     fp32 unless stated; no hidden allocation, no global mutable state, re-entrant
+ *     across the forward and autograd threads;
+ *   - every call takes the CUDA stream to launch on (a cudaStream_t passed as void*)
+ *     and never synchronises the host;
+ *   - return 0 on success, a negative KT_ERR_* code otherwise (the Python wrapper
+ *     raises RuntimeError with kt_last_error()).
+ *
+ * ACTIVATION LAYOUT: channels-last rows.  A logical (B, C, T) tensor of the reference
+ * is stored as [B][T][nsub][C] with C contiguous ("row" = one time step of one
+ * sub-sequence).  nsub = 1 everywhere except the period discriminator, where the
+ * reference's (B, C, T/p, p) view (hifigan.py:258) is stored as [B][T/p][p][C] and the
+ * (k,1) Conv2d becomes a Conv1d over the p interleaved sub-sequences.
+ */
+#ifndef KANTTS_B200_H_
+#define KANTTS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KT_OK 0
+#define KT_ERR_INVALID -1   /* bad descriptor / unsupported combination */
+#define KT_ERR_CUDA -2      /* a CUDA runtime call or launch failed */
+#define KT_ERR_WORKSPACE -3 /* workspace too small */
+
+/* activation codes */
+#define KT_ACT_NONE 0
+#define KT_ACT_LRELU 1 /* leaky relu, slope in the descriptor */
+#define KT_ACT_TANH 2  /* output side only */
+
+/* compute paths */
+#define KT_PATH_AUTO 0  /* tcgen05 where the shape qualifies, FFMA otherwise */
+#define KT_PATH_FFMA 1  /* exact-fp32 CUDA-core kernels */
+#define KT_PATH_TC 2    /* tcgen05 split-bf16 (bf16x3) tensor-core kernels; error if unsupported */
+
+/* One 1-D convolution layer (forward semantics; the backward entry points take the
+ * SAME descriptor).  Replaces F.conv1d / F.conv_transpose1d / F.conv2d((k,1)) as
+ * dispatched from kantts/models/hifigan/layers.py:44-46,82-88,123,161 and
+ * hifigan.py:219-247,328-396 (cuDNN fwd / dgrad / wgrad).
+ *
+ *   conv       : y[b,to,co] = act_out( bias[co] + sum_{j,ci} w[co,ci,j] * act_in(xu[b, to*stride + j*dilation - pad_left, ci]) ) + resid
+ *                xu = x nearest-upsampled by `upsample` (hifigan.py:85: nn.Upsample) ; out-of-range taps read 0
+ *   transposed : y[b, ti*stride + j*dilation - pad_left, co] += w[ci,co,j] * act_in(x[b,ti,ci])   (then bias, act_out, resid)
+ *   t_out is given explicitly (the causal variants crop: layers.py:87,161).
+ */
+typedef struct KtConv1dDesc {
+  int32_t batch;      /* B */
+  int32_t nsub;       /* interleaved sub-sequences per batch item (period p; else 1) */
+  int32_t t_in;       /* input time steps per sub-sequence */
+  int32_t t_out;      /* output time steps per sub-sequence */
+  int32_t c_in;
+  int32_t c_out;
+  int32_t groups;
+  int32_t kernel;
+  int32_t stride;
+  int32_t dilation;
+  int32_t pad_left;
+  int32_t transposed; /* 0 conv, 1 ConvTranspose1d */
+  int32_t upsample;   /* >=1; nearest-neighbour upsampling of the input (conv only) */
+  int32_t act_in;     /* KT_ACT_NONE | KT_ACT_LRELU */
+  float act_in_slope;
+  int32_t act_out;    /* KT_ACT_NONE | KT_ACT_LRELU | KT_ACT_TANH */
+  float act_out_slope;
+  int32_t path;       /* KT_PATH_* */
+} KtConv1dDesc;
+
+/* Weight layouts consumed by the conv kernels ("kernel layouts"), produced by
+ * kt_weight_prepare from the reference parameter layout:
+ *   conv       reference (Cout, Cin/g, k):  w_fwd[k][Cin/g][Cout]   w_bwd[k][Cout/g][Cin]
+ *   transposed reference (Cin, Cout, k)  :  w_fwd[k][Cin][Cout]     w_bwd[k][Cout][Cin]
+ * Both are fp32; kt_weight_pack_tc turns either into the split-bf16 tiles of the tcgen05 path. */
+
+/* Weight re-parametrisation + layout (replaces torch._weight_norm at layers.py:29,67,
+ * 105,139 and hifigan.py:224,331; plain / spectral-normed weights use mode 0 with an
+ * optional device scalar `inv_sigma`).
+ *   mode 1 (weight norm, dim 0): w = g[d0] * v / ||v[d0,:,:]||   ; norm_out[d0] = ||v[d0]||
+ *   mode 0 (plain)             : w = v * (inv_sigma ? *inv_sigma : 1)
+ * v is the reference layout (d0, d1, k); `transposed` says whether d0 is Cin (1) or Cout (0);
+ * `groups` as in the conv (d1 = Cin/groups).  w_ref (optional) receives w in reference layout. */
+int kt_weight_prepare(const float* v, const float* g, const float* inv_sigma, int32_t mode,
+                      int32_t d0, int32_t d1, int32_t k, int32_t transposed, int32_t groups,
+                      float* w_fwd, float* w_bwd, float* norm_out, float* w_ref, void* stream);
+
+/* Backward of kt_weight_prepare: dw_fwd is in the layout written by kt_conv1d_bwd_weight
+ * (w_fwd layout for a conv, w_bwd layout for a transposed conv).  mode 1: dv, dg (reference layouts);  mode 0: dv = dw * scale. */
+int kt_weight_grad(const float* dw_fwd, const float* v, const float* g, const float* norm,
+                   const float* inv_sigma, int32_t mode, int32_t d0, int32_t d1, int32_t k,
+                   int32_t transposed, int32_t groups, float* dv, float* dg, void* stream);
+
+/* Forward.  x: [B][t_in][nsub][c_in], y: [B][t_out][nsub][c_out]; bias / resid optional (NULL).
+ * resid has y's shape and is added AFTER act_out (layers.py:219 `x = xt + x`; hifigan.py:168). */
+int kt_conv1d_fwd(const KtConv1dDesc* d, const float* x, const float* w_fwd, const float* bias,
+                  const float* resid, float* y, void* stream);
+
+/* Data gradient.  dy: gradient wrt y; y: the forward output (needed when act_out != NONE,
+ * to apply act_out'), x: the forward input (needed when act_in != NONE).  dx is overwritten. */
+int kt_conv1d_bwd_data(const KtConv1dDesc* d, const float* dy, const float* y, const float* w_bwd,
+                       const float* x, float* dx, void* stream);
+
+/* Weight / bias gradient.  dw (k*Cin/g*Cout floats; w_fwd layout for a conv, w_bwd layout
+ * [k][Cout][Cin] for a transposed conv) and dbias (c_out, optional) are overwritten.  */
+int kt_conv1d_bwd_weight(const KtConv1dDesc* d, const float* x, const float* dy, const float* y,
+                         float* dw, float* dbias, void* stream);
+
+/* ---- tcgen05 (5th-gen tensor core) path: bf16x3 split-precision implicit GEMM, fp32 accumulation in TMEM ----
+ * kt_conv1d_tc_plan: returns the output-channel tile NT (> 0) when direction `dir` (0 forward, 1 data
+ * gradient) of the layer can run on the tcgen05 kernel (groups 1, contraction channels % 64 == 0,
+ * produced channels % 16 == 0, unit input step), else 0.
+ * kt_weight_pack_tc: fp32 kernel-layout weights W[taps][K][N] (w_fwd for dir 0, w_bwd for dir 1) ->
+ * hi/lo bf16 SWIZZLE_128B tiles ([taps][K/64][N/NT][2][NT][64] bf16, i.e. taps*K*N*4 bytes).
+ * kt_conv1d_{fwd,bwd_data}_tc: same contract as the fp32 entry points, `wimg` = the packed tiles. */
+int kt_conv1d_tc_plan(const KtConv1dDesc* d, int32_t dir);
+int kt_weight_pack_tc(const float* w, int32_t taps, int32_t k_dim, int32_t n_dim, int32_t n_tile, void* out, void* stream);
+int kt_conv1d_fwd_tc(const KtConv1dDesc* d, const float* x, const void* wimg, const float* bias, const float* resid,
+                     float* y, void* stream);
+int kt_conv1d_bwd_data_tc(const KtConv1dDesc* d, const float* dy, const float* y, const void* wimg, const float* x,
+                          float* dx, void* stream);
+
+/* Elementwise pieces of Generator.forward (hifigan.py:157 `x = sin(x) + x`). */
+int kt_sinadd_fwd(const float* x, float* y, int64_t n, void* stream);
+int kt_sinadd_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream);
+/* y = scale * (a + b + c)   (hifigan.py:170-176: mean over the resblocks; b, c optional) */
+int kt_add3_scale(const float* a, const float* b, const float* c, float scale, float* y, int64_t n, void* stream);
+
+/* db3 single-level analysis DWT, zero padding (pytorch_wavelets.DWT1DForward as used at
+ * hifigan.py:445-448,469-471) fused with torch.cat([yl, yh], dim=1): x [B][T] -> y [B][T2][2]
+ * with T2 = (T + 5) / 2, channel 0 = low-pass, 1 = high-pass. */
+int kt_dwt_db3_fwd(const float* x, float* y, int32_t batch, int32_t t, void* stream);
+int kt_dwt_db3_bwd(const float* dy, float* dx, int32_t batch, int32_t t, void* stream);
+
+/* Fused mel-spectrogram (kantts/utils/audio_torch.py:155-186): centre zero-padded framing,
+ * periodic-hann window, rFFT, sqrt(clamp(|.|^2, eps)), mel projection, clamp(eps),
+ * 20*log10(clamp(.,1e-5)) - 20, clamp(8*(x+100)/100 - 4, -4, 4).
+ *   wav  [B][T]            mel [B][n_mels][frames] (reference layout)
+ *   melmat [n_bins][n_mels] (n_bins = n_fft/2+1), window [n_fft] (a shorter win_length is centre-padded by the caller).
+ * n_fft must be a power of two in [64, 4096] (all shipped configs: 512 / 1024 / 2048). */
+typedef struct KtMelDesc {
+  int32_t batch, t, n_fft, hop, n_mels, frames; /* frames = t / hop + 1 (center=True) */
+  int32_t pad_mode;                              /* 0 zeros (MelSpectrogram), 1 reflect (stft()) */
+  float eps;                                     /* 1e-10 (mel) / 1e-7 (stft loss) */
+} KtMelDesc;
+/* Outputs (each optional / NULL): mel [B][n_mels][frames] (needs melmat), amp [B][frames][n_bins]
+ * (the clamped magnitude, audio_torch.py:31), spec [B][frames][n_bins][2] (re, im; saved for bwd). */
+int kt_stft_mel_fwd(const KtMelDesc* d, const float* wav, const float* window, const float* melmat,
+                    float* mel, float* amp, float* spec, void* stream);
+/* dwav [B][T] (overwritten) = d/dwav of sum(dmel * mel) + sum(damp * amp); dmel / damp optional. */
+int kt_stft_mel_bwd(const KtMelDesc* d, const float* dmel, const float* damp, const float* spec,
+                    const float* window, const float* melmat, float* dwav, void* stream);
+
+/* out[0] = scale * sum |a - b|  (F.l1_loss numerator; loss.py:249,309); out[0] is overwritten. */
+int kt_l1_sum(const float* a, const float* b, int64_t n, float scale, float* out, void* stream);
+
+/* library info */
+const char* kt_last_error(void);
+int kt_version(void);
+/* 1 when the library was built with the tcgen05 (sm_100a) conv path */
+int kt_has_tc(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KANTTS_B200_H_ */

@@ -1,0 +1,128 @@
+"""ctypes binding of libkantts_b200.so (the C ABI declared in include/kantts_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``kantts_b200.build_library()``
+(nvcc, sm_100a).  There is NO fallback: if the shared object is missing or a call fails, a
+RuntimeError is raised -- the product path never routes through PyTorch library kernels or
+the CPU oracle.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkantts_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+SOURCES = ["api.cu", "conv_ffma.cu", "conv_tc.cu", "weights.cu", "misc.cu", "stft_mel.cu"]
+
+KT_ACT_NONE, KT_ACT_LRELU, KT_ACT_TANH = 0, 1, 2
+KT_PATH_AUTO, KT_PATH_FFMA, KT_PATH_TC = 0, 1, 2
+
+
+class KtConv1dDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("batch", "nsub", "t_in", "t_out", "c_in", "c_out", "groups", "kernel", "stride",
+                 "dilation", "pad_left", "transposed", "upsample", "act_in")] + \
+               [("act_in_slope", ctypes.c_float), ("act_out", ctypes.c_int32),
+                ("act_out_slope", ctypes.c_float), ("path", ctypes.c_int32)]
+
+
+class KtMelDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("batch", "t", "n_fft", "hop", "n_mels", "frames", "pad_mode")] + \
+               [("eps", ctypes.c_float)]
+
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int32
+_L = ctypes.c_int64
+_F = ctypes.c_float
+
+# name -> argtypes; mirrors include/kantts_b200.h one to one
+PROTOTYPES = {
+    "kt_weight_prepare": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "kt_weight_grad": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "kt_conv1d_fwd": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P],
+    "kt_conv1d_bwd_data": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P],
+    "kt_conv1d_bwd_weight": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P],
+    "kt_sinadd_fwd": [_P, _P, _L, _P],
+    "kt_sinadd_bwd": [_P, _P, _P, _L, _P],
+    "kt_add3_scale": [_P, _P, _P, _F, _P, _L, _P],
+    "kt_dwt_db3_fwd": [_P, _P, _I, _I, _P],
+    "kt_dwt_db3_bwd": [_P, _P, _I, _I, _P],
+    "kt_stft_mel_fwd": [ctypes.POINTER(KtMelDesc), _P, _P, _P, _P, _P, _P, _P],
+    "kt_stft_mel_bwd": [ctypes.POINTER(KtMelDesc), _P, _P, _P, _P, _P, _P, _P],
+    "kt_l1_sum": [_P, _P, _L, _F, _P, _P],
+    "kt_conv1d_tc_plan": [ctypes.POINTER(KtConv1dDesc), _I],
+    "kt_weight_pack_tc": [_P, _I, _I, _I, _I, _P, _P],
+    "kt_conv1d_fwd_tc": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P],
+    "kt_conv1d_bwd_data_tc": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P],
+    "kt_version": [],
+    "kt_has_tc": [],
+}
+
+_lib = None
+
+
+def nvcc_command(out_path=LIB_PATH):
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    return ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+            "-Xcompiler", "-fPIC", "-shared", "-o", out_path] + srcs + ["-lcuda"]
+
+
+def build_library(force=False, verbose=False):
+    """Compile libkantts_b200.so in-tree for sm_100a (cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    deps = srcs + [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_common.cuh"),
+                   os.path.join(os.path.dirname(_HERE), "include", "kantts_b200.h")]
+    deps = [d for d in deps if os.path.exists(d)]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    cmd = nvcc_command()
+    if verbose:
+        print(" ".join(cmd), file=sys.stderr)
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return LIB_PATH
+
+
+def load():
+    """-> the ctypes library handle; raises if the shared object is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). kantts_b200 has no CPU / PyTorch fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in PROTOTYPES.items():
+        fn = getattr(lib, name)            # AttributeError here = header / library mismatch
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    lib.kt_last_error.argtypes = []
+    lib.kt_last_error.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().kt_last_error().decode(errors="replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """device pointer of a tensor (None -> NULL); the tensor must be CUDA, fp32, contiguous."""
+    if t is None:
+        return None
+    if not (t.is_cuda and t.is_contiguous()):
+        raise RuntimeError(f"kantts_b200: expected a contiguous CUDA tensor, got device={t.device} "
+                           f"contiguous={t.is_contiguous()} (no CPU fallback)")
+    return t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,114 @@
+// extern "C" surface of libkantts_b200.so (see include/kantts_b200.h).
+#include "common.cuh"
+
+namespace kt {
+const char* last_error();
+int validate_conv(const KtConv1dDesc* d);
+int conv1d_fwd_ffma(const KtConv1dDesc*, const float*, const float*, const float*, const float*, float*, cudaStream_t);
+int conv1d_bwd_data_ffma(const KtConv1dDesc*, const float*, const float*, const float*, const float*, float*, cudaStream_t);
+int conv1d_bwd_weight_ffma(const KtConv1dDesc*, const float*, const float*, const float*, float*, float*, cudaStream_t);
+int weight_prepare(const float*, const float*, const float*, int, int, int, int, int, int, float*, float*, float*, float*, cudaStream_t);
+int weight_grad(const float*, const float*, const float*, const float*, const float*, int, int, int, int, int, int, float*, float*, cudaStream_t);
+int sinadd_fwd(const float*, float*, long long, cudaStream_t);
+int sinadd_bwd(const float*, const float*, float*, long long, cudaStream_t);
+int add3_scale(const float*, const float*, const float*, float, float*, long long, cudaStream_t);
+int dwt_fwd(const float*, float*, int, int, cudaStream_t);
+int dwt_bwd(const float*, float*, int, int, cudaStream_t);
+int l1_sum(const float*, const float*, long long, float, float*, cudaStream_t);
+int stft_mel_fwd(const KtMelDesc*, const float*, const float*, const float*, float*, float*, float*, cudaStream_t);
+int stft_mel_bwd(const KtMelDesc*, const float*, const float*, const float*, const float*, const float*, float*, cudaStream_t);
+int tc_plan(const KtConv1dDesc*, int);
+int tc_pack_weights(const float*, int, int, int, int, void*, cudaStream_t);
+int conv1d_fwd_tc(const KtConv1dDesc*, const float*, const void*, const float*, const float*, float*, cudaStream_t);
+int conv1d_bwd_data_tc(const KtConv1dDesc*, const float*, const float*, const void*, const float*, float*, cudaStream_t);
+}  // namespace kt
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int kt_weight_prepare(const float* v, const float* g, const float* inv_sigma, int32_t mode, int32_t d0, int32_t d1,
+                      int32_t k, int32_t transposed, int32_t groups, float* w_fwd, float* w_bwd, float* norm_out,
+                      float* w_ref, void* stream) {
+  return kt::weight_prepare(v, g, inv_sigma, mode, d0, d1, k, transposed, groups, w_fwd, w_bwd, norm_out, w_ref, ST(stream));
+}
+
+int kt_weight_grad(const float* dw_fwd, const float* v, const float* g, const float* norm, const float* inv_sigma,
+                   int32_t mode, int32_t d0, int32_t d1, int32_t k, int32_t transposed, int32_t groups, float* dv,
+                   float* dg, void* stream) {
+  return kt::weight_grad(dw_fwd, v, g, norm, inv_sigma, mode, d0, d1, k, transposed, groups, dv, dg, ST(stream));
+}
+
+int kt_conv1d_fwd(const KtConv1dDesc* d, const float* x, const float* w_fwd, const float* bias, const float* resid,
+                  float* y, void* stream) {
+  int rc = kt::validate_conv(d);
+  if (rc) return rc;
+  KT_REQUIRE(x && w_fwd && y, "kt_conv1d_fwd: null pointer");
+  KT_REQUIRE(d->path != KT_PATH_TC, "kt_conv1d_fwd: tcgen05 path not available for this shape");
+  return kt::conv1d_fwd_ffma(d, x, w_fwd, bias, resid, y, ST(stream));
+}
+
+int kt_conv1d_bwd_data(const KtConv1dDesc* d, const float* dy, const float* y, const float* w_bwd, const float* x,
+                       float* dx, void* stream) {
+  int rc = kt::validate_conv(d);
+  if (rc) return rc;
+  KT_REQUIRE(dy && w_bwd && dx, "kt_conv1d_bwd_data: null pointer");
+  KT_REQUIRE(d->path != KT_PATH_TC, "kt_conv1d_bwd_data: tcgen05 path not available for this shape");
+  return kt::conv1d_bwd_data_ffma(d, dy, y, w_bwd, x, dx, ST(stream));
+}
+
+int kt_conv1d_bwd_weight(const KtConv1dDesc* d, const float* x, const float* dy, const float* y, float* dw,
+                         float* dbias, void* stream) {
+  int rc = kt::validate_conv(d);
+  if (rc) return rc;
+  KT_REQUIRE(x && dy && dw, "kt_conv1d_bwd_weight: null pointer");
+  KT_REQUIRE(d->path != KT_PATH_TC, "kt_conv1d_bwd_weight: tcgen05 path not available for this shape");
+  return kt::conv1d_bwd_weight_ffma(d, x, dy, y, dw, dbias, ST(stream));
+}
+
+int kt_sinadd_fwd(const float* x, float* y, int64_t n, void* stream) { return kt::sinadd_fwd(x, y, n, ST(stream)); }
+int kt_sinadd_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream) { return kt::sinadd_bwd(x, dy, dx, n, ST(stream)); }
+int kt_add3_scale(const float* a, const float* b, const float* c, float scale, float* y, int64_t n, void* stream) {
+  return kt::add3_scale(a, b, c, scale, y, n, ST(stream));
+}
+int kt_dwt_db3_fwd(const float* x, float* y, int32_t batch, int32_t t, void* stream) { return kt::dwt_fwd(x, y, batch, t, ST(stream)); }
+int kt_dwt_db3_bwd(const float* dy, float* dx, int32_t batch, int32_t t, void* stream) { return kt::dwt_bwd(dy, dx, batch, t, ST(stream)); }
+int kt_stft_mel_fwd(const KtMelDesc* d, const float* wav, const float* window, const float* melmat, float* mel,
+                    float* amp, float* spec, void* stream) {
+  return kt::stft_mel_fwd(d, wav, window, melmat, mel, amp, spec, ST(stream));
+}
+int kt_stft_mel_bwd(const KtMelDesc* d, const float* dmel, const float* damp, const float* spec, const float* window,
+                    const float* melmat, float* dwav, void* stream) {
+  return kt::stft_mel_bwd(d, dmel, damp, spec, window, melmat, dwav, ST(stream));
+}
+int kt_l1_sum(const float* a, const float* b, int64_t n, float scale, float* out, void* stream) {
+  return kt::l1_sum(a, b, n, scale, out, ST(stream));
+}
+
+const char* kt_last_error(void) { return kt::last_error(); }
+int kt_version(void) { return 1; }
+int kt_has_tc(void) { return 1; }
+
+int kt_conv1d_tc_plan(const KtConv1dDesc* d, int32_t dir) {
+  if (kt::validate_conv(d)) return 0;
+  return kt::tc_plan(d, dir);
+}
+int kt_weight_pack_tc(const float* w, int32_t taps, int32_t k_dim, int32_t n_dim, int32_t n_tile, void* out, void* stream) {
+  return kt::tc_pack_weights(w, taps, k_dim, n_dim, n_tile, out, ST(stream));
+}
+int kt_conv1d_fwd_tc(const KtConv1dDesc* d, const float* x, const void* wimg, const float* bias, const float* resid,
+                     float* y, void* stream) {
+  int rc = kt::validate_conv(d);
+  if (rc) return rc;
+  KT_REQUIRE(x && wimg && y, "kt_conv1d_fwd_tc: null pointer");
+  return kt::conv1d_fwd_tc(d, x, wimg, bias, resid, y, ST(stream));
+}
+int kt_conv1d_bwd_data_tc(const KtConv1dDesc* d, const float* dy, const float* y, const void* wimg, const float* x,
+                          float* dx, void* stream) {
+  int rc = kt::validate_conv(d);
+  if (rc) return rc;
+  KT_REQUIRE(dy && wimg && dx, "kt_conv1d_bwd_data_tc: null pointer");
+  return kt::conv1d_bwd_data_tc(d, dy, y, wimg, x, dx, ST(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,360 @@
+"""torch.autograd.Function wrappers over the C ABI (include/kantts_b200.h).
+
+Internal activation layout: channels-last rows, ``(B, T, C)`` contiguous fp32 (``(B, T, p, C)``
+for the period discriminator).  The nn.Modules in hifigan.py convert at their boundary only.
+Backward functions run on the autograd engine thread; every call passes the thread's current
+stream explicitly and the library keeps no global state.
+"""
+import ctypes
+import os
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _lib
+from ._lib import (KT_ACT_LRELU, KT_ACT_NONE, KT_ACT_TANH, KT_PATH_AUTO, KT_PATH_FFMA, KT_PATH_TC, KtConv1dDesc, KtMelDesc, check, ptr,
+                   stream_ptr)
+
+_launches = 0          # kernels-launched counter (bench.py reports it as gpu_launches)
+
+
+def launch_count():
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+@dataclass
+class ConvSpec:
+    """Static description of one conv layer (forward semantics), see KtConv1dDesc."""
+    c_in: int
+    c_out: int
+    kernel: int
+    stride: int = 1
+    dilation: int = 1
+    pad_left: int = 0
+    pad_right: int = 0          # only used to derive t_out
+    groups: int = 1
+    transposed: bool = False
+    upsample: int = 1
+    crop: int = 0               # transposed: samples cropped from the end (causal variant, layers.py:161)
+    act_in: int = KT_ACT_NONE
+    act_in_slope: float = 0.0
+    act_out: int = KT_ACT_NONE
+    act_out_slope: float = 0.0
+    path: int = KT_PATH_AUTO
+    _descs: dict = field(default_factory=dict, repr=False)
+
+    def t_out(self, t_in):
+        if self.transposed:
+            return (t_in - 1) * self.stride - 2 * self.pad_left + self.dilation * (self.kernel - 1) + 1 - self.crop
+        t = t_in * self.upsample
+        return (t + self.pad_left + self.pad_right - self.dilation * (self.kernel - 1) - 1) // self.stride + 1
+
+    def desc(self, batch, nsub, t_in):
+        key = (batch, nsub, t_in)
+        d = self._descs.get(key)
+        if d is None:
+            d = KtConv1dDesc(batch=batch, nsub=nsub, t_in=t_in, t_out=self.t_out(t_in), c_in=self.c_in,
+                             c_out=self.c_out, groups=self.groups, kernel=self.kernel, stride=self.stride,
+                             dilation=self.dilation, pad_left=self.pad_left, transposed=int(self.transposed),
+                             upsample=self.upsample, act_in=self.act_in, act_in_slope=self.act_in_slope,
+                             act_out=self.act_out, act_out_slope=self.act_out_slope, path=self.path)
+            self._descs[key] = d
+        return d
+
+    @property
+    def w_numel(self):
+        return self.kernel * (self.c_in // self.groups) * self.c_out
+
+
+class PreparedWeight:
+    """Kernel-layout copies of one layer's effective weight (w_fwd, w_bwd) + the weight-norm
+    row norms, valid for one (parameter version) -- see kt_weight_prepare."""
+
+    __slots__ = ("w_fwd", "w_bwd", "norm", "key", "img")
+
+    def __init__(self):
+        self.w_fwd = self.w_bwd = self.norm = None
+        self.key = None
+        self.img = {}          # (dir, n_tile) -> packed split-bf16 tcgen05 weight tiles
+
+    def tc_image(self, spec, direction, n_tile):
+        """hi/lo bf16 SWIZZLE_128B weight tiles for the tcgen05 kernels (kt_weight_pack_tc)."""
+        k = (direction, n_tile)
+        img = self.img.get(k)
+        if img is None:
+            cin_g = spec.c_in // spec.groups
+            # contraction dim K / produced dim N of this direction's GEMM
+            kdim, ndim = (cin_g, spec.c_out) if direction == 0 else (spec.c_out // spec.groups, spec.c_in)
+            src = self.w_fwd if direction == 0 else self.w_bwd
+            img = torch.empty(spec.kernel * kdim * ndim * 2, device=src.device, dtype=torch.bfloat16)
+            check(_lib.load().kt_weight_pack_tc(ptr(src), spec.kernel, kdim, ndim, n_tile, ptr(img), stream_ptr()),
+                  "kt_weight_pack_tc")
+            _count()
+            self.img[k] = img
+        return img
+
+
+def prepare_weight(cache, spec, v, g):
+    """v: reference-layout weight (weight_v for weight-norm, the effective weight otherwise);
+    g: weight_g or None.  Re-runs the prepare kernel only when a parameter changed."""
+    # only leaf parameters have a trustworthy (data_ptr, version) identity; a recomputed
+    # spectral-norm weight is a fresh tensor every forward and is never cached
+    cacheable = v.is_leaf and (g is None or g.is_leaf)
+    key = (v.data_ptr(), v._version, None if g is None else (g.data_ptr(), g._version)) if cacheable else None
+    if key is not None and cache.key == key and cache.w_fwd is not None and cache.w_fwd.device == v.device:
+        return cache
+    lib = _lib.load()
+    d0 = v.shape[0]
+    d1 = v.shape[1]
+    k = spec.kernel
+    assert v.numel() == d0 * d1 * k, (v.shape, spec)
+    vd = v.detach()
+    if not vd.is_contiguous():
+        vd = vd.contiguous()
+    cache.w_fwd = torch.empty(spec.w_numel, device=v.device, dtype=torch.float32)
+    cache.w_bwd = torch.empty(spec.w_numel, device=v.device, dtype=torch.float32)
+    mode = 0 if g is None else 1
+    cache.norm = torch.empty(d0, device=v.device, dtype=torch.float32) if mode else None
+    gd = None if g is None else g.detach().contiguous()
+    check(lib.kt_weight_prepare(ptr(vd), ptr(gd), None, mode, d0, d1, k, int(spec.transposed), spec.groups,
+                                ptr(cache.w_fwd), ptr(cache.w_bwd), ptr(cache.norm), None, stream_ptr()),
+          "kt_weight_prepare")
+    _count()
+    cache.key = key
+    cache.img = {}
+    return cache
+
+
+_FORCE_FFMA = os.environ.get("KANTTS_B200_PATH", "").lower() == "ffma"
+_tc_launches = 0
+
+
+def tc_launch_count():
+    return _tc_launches
+
+
+def set_force_ffma(flag):
+    """Route every conv through the exact-fp32 FFMA kernels (A/B testing of the tcgen05 path)."""
+    global _FORCE_FFMA
+    _FORCE_FFMA = bool(flag)
+
+
+def _tc_tile(lib, spec, d, direction):
+    if _FORCE_FFMA or spec.path == KT_PATH_FFMA:
+        return 0
+    key = ("tc", direction, d.batch, d.nsub, d.t_in)
+    nt = spec._descs.get(key)
+    if nt is None:
+        nt = lib.kt_conv1d_tc_plan(ctypes.byref(d), direction)
+        spec._descs[key] = nt
+    if nt == 0 and spec.path == KT_PATH_TC:
+        raise RuntimeError(f"kantts_b200: layer {spec} cannot run on the tcgen05 path")
+    return nt
+
+
+class ConvFn(torch.autograd.Function):
+    """y = act_out(conv(act_in(x)) + bias) + resid   on channels-last rows."""
+
+    @staticmethod
+    def forward(ctx, x, resid, bias, v, g, spec, cache):
+        lib = _lib.load()
+        x = x.contiguous()
+        nsub = x.shape[2] if x.dim() == 4 else 1
+        B, t_in = x.shape[0], x.shape[1]
+        assert x.shape[-1] == spec.c_in, (x.shape, spec)
+        d = spec.desc(B, nsub, t_in)
+        pw = prepare_weight(cache, spec, v, g)
+        shape = (B, d.t_out, nsub, spec.c_out) if x.dim() == 4 else (B, d.t_out, spec.c_out)
+        y = torch.empty(shape, device=x.device, dtype=torch.float32)
+        if resid is not None:
+            resid = resid.contiguous()
+            assert resid.shape == y.shape, (resid.shape, y.shape)
+        bd = None if bias is None else bias.detach()
+        nt = _tc_tile(lib, spec, d, 0)
+        if nt:
+            global _tc_launches
+            check(lib.kt_conv1d_fwd_tc(ctypes.byref(d), ptr(x), ptr(pw.tc_image(spec, 0, nt)), ptr(bd), ptr(resid),
+                                       ptr(y), stream_ptr()), "kt_conv1d_fwd_tc")
+            _tc_launches += spec.stride if spec.transposed else 1
+        else:
+            check(lib.kt_conv1d_fwd(ctypes.byref(d), ptr(x), ptr(pw.w_fwd), ptr(bd), ptr(resid), ptr(y), stream_ptr()),
+                  "kt_conv1d_fwd")
+        _count(spec.stride if spec.transposed else 1)
+        ctx.spec, ctx.d = spec, d
+        ctx.w_bwd, ctx.norm = pw.w_bwd, pw.norm
+        nt_b = _tc_tile(lib, spec, d, 1) if x.requires_grad else 0
+        ctx.nt_bwd = nt_b
+        ctx.img_bwd = pw.tc_image(spec, 1, nt_b) if nt_b else None
+        ctx.has_resid, ctx.has_bias, ctx.has_g = resid is not None, bias is not None, g is not None
+        ctx.save_for_backward(x, y if spec.act_out != KT_ACT_NONE else None, v, g)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, y, v, g = ctx.saved_tensors
+        spec, d = ctx.spec, ctx.d
+        dy = dy.contiguous()
+        st = stream_ptr()
+        dx = dres = dbias = dv = dg = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            if ctx.nt_bwd:
+                global _tc_launches
+                check(lib.kt_conv1d_bwd_data_tc(ctypes.byref(d), ptr(dy), ptr(y), ptr(ctx.img_bwd), ptr(x), ptr(dx), st),
+                      "kt_conv1d_bwd_data_tc")
+                _tc_launches += 1
+            else:
+                check(lib.kt_conv1d_bwd_data(ctypes.byref(d), ptr(dy), ptr(y), ptr(ctx.w_bwd), ptr(x), ptr(dx), st),
+                      "kt_conv1d_bwd_data")
+            _count(max(spec.stride if not spec.transposed else 1, spec.upsample))
+        if ctx.has_resid and ctx.needs_input_grad[1]:
+            dres = dy
+        need_w = ctx.needs_input_grad[3] or (ctx.has_g and ctx.needs_input_grad[4])
+        need_b = ctx.has_bias and ctx.needs_input_grad[2]
+        if need_w or need_b:
+            dw = torch.empty(spec.w_numel, device=x.device, dtype=torch.float32)
+            if need_b:
+                dbias = torch.empty(spec.c_out, device=x.device, dtype=torch.float32)
+            check(lib.kt_conv1d_bwd_weight(ctypes.byref(d), ptr(x), ptr(dy), ptr(y), ptr(dw), ptr(dbias), st),
+                  "kt_conv1d_bwd_weight")
+            _count(4 if need_b else 2)
+            if need_w:
+                vd = v.detach().contiguous()
+                dv = torch.empty_like(vd)
+                if ctx.has_g:
+                    dg = torch.empty_like(g)
+                check(lib.kt_weight_grad(ptr(dw), ptr(vd), ptr(None if g is None else g.detach().contiguous()),
+                                         ptr(ctx.norm), None, 1 if ctx.has_g else 0, vd.shape[0], vd.shape[1],
+                                         spec.kernel, int(spec.transposed), spec.groups, ptr(dv), ptr(dg), st),
+                      "kt_weight_grad")
+                _count()
+        return dx, dres, dbias, dv, dg, None, None
+
+
+def conv(x, spec, cache, v, g=None, bias=None, resid=None):
+    return ConvFn.apply(x, resid, bias, v, g, spec, cache)
+
+
+class SinAddFn(torch.autograd.Function):
+    """hifigan.py:157  x = sin(x) + x"""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        check(_lib.load().kt_sinadd_fwd(ptr(x), ptr(y), x.numel(), stream_ptr()), "kt_sinadd_fwd")
+        _count()
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        check(_lib.load().kt_sinadd_bwd(ptr(x), ptr(dy), ptr(dx), x.numel(), stream_ptr()), "kt_sinadd_bwd")
+        _count()
+        return dx
+
+
+class Mean3Fn(torch.autograd.Function):
+    """hifigan.py:170-176  mean over the parallel resblocks: scale * (a + b + c)."""
+
+    @staticmethod
+    def forward(ctx, scale, a, b, c):
+        a = a.contiguous()
+        b = None if b is None else b.contiguous()
+        c = None if c is None else c.contiguous()
+        y = torch.empty_like(a)
+        check(_lib.load().kt_add3_scale(ptr(a), ptr(b), ptr(c), float(scale), ptr(y), a.numel(), stream_ptr()),
+              "kt_add3_scale")
+        _count()
+        ctx.scale, ctx.nb, ctx.nc = scale, b is not None, c is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        g = torch.empty_like(dy)
+        check(_lib.load().kt_add3_scale(ptr(dy), None, None, float(ctx.scale), ptr(g), dy.numel(), stream_ptr()),
+              "kt_add3_scale")
+        _count()
+        return None, g, (g if ctx.nb else None), (g if ctx.nc else None)
+
+
+class DwtFn(torch.autograd.Function):
+    """db3 analysis + channel concat: (B, T) -> (B, (T+5)//2, 2)   (hifigan.py:469-470)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        B, T = x.shape
+        y = torch.empty(B, (T + 5) // 2, 2, device=x.device, dtype=torch.float32)
+        check(_lib.load().kt_dwt_db3_fwd(ptr(x), ptr(y), B, T, stream_ptr()), "kt_dwt_db3_fwd")
+        _count()
+        ctx.shape = (B, T)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, T = ctx.shape
+        dy = dy.contiguous()
+        dx = torch.empty(B, T, device=dy.device, dtype=torch.float32)
+        check(_lib.load().kt_dwt_db3_bwd(ptr(dy), ptr(dx), B, T, stream_ptr()), "kt_dwt_db3_bwd")
+        _count()
+        return dx
+
+
+class StftMelFn(torch.autograd.Function):
+    """Fused framing/window/rFFT/magnitude(/mel/log-normalise).  Returns mel (B, n_mels, frames)
+    when ``melmat`` is given, else the magnitude (B, frames, n_bins)."""
+
+    @staticmethod
+    def forward(ctx, wav, window, melmat, n_fft, hop, pad_mode, eps):
+        wav = wav.contiguous()
+        B, T = wav.shape
+        frames = T // hop + 1
+        nb = n_fft // 2 + 1
+        n_mels = 0 if melmat is None else melmat.shape[1]
+        d = KtMelDesc(batch=B, t=T, n_fft=n_fft, hop=hop, n_mels=n_mels, frames=frames, pad_mode=pad_mode, eps=eps)
+        spec = torch.empty(B, frames, nb, 2, device=wav.device, dtype=torch.float32) \
+            if ctx.needs_input_grad[0] else None
+        mel = amp = None
+        if melmat is not None:
+            mel = torch.empty(B, n_mels, frames, device=wav.device, dtype=torch.float32)
+        else:
+            amp = torch.empty(B, frames, nb, device=wav.device, dtype=torch.float32)
+        check(_lib.load().kt_stft_mel_fwd(ctypes.byref(d), ptr(wav), ptr(window), ptr(melmat), ptr(mel), ptr(amp),
+                                         ptr(spec), stream_ptr()), "kt_stft_mel_fwd")
+        _count()
+        ctx.d = d
+        ctx.is_mel = melmat is not None
+        ctx.save_for_backward(spec, window, melmat)
+        return mel if melmat is not None else amp
+
+    @staticmethod
+    def backward(ctx, dout):
+        spec, window, melmat = ctx.saved_tensors
+        d = ctx.d
+        dout = dout.contiguous()
+        dwav = torch.empty(d.batch, d.t, device=dout.device, dtype=torch.float32)
+        dmel, damp = (dout, None) if ctx.is_mel else (None, dout)
+        check(_lib.load().kt_stft_mel_bwd(ctypes.byref(d), ptr(dmel), ptr(damp), ptr(spec), ptr(window), ptr(melmat),
+                                         ptr(dwav), stream_ptr()), "kt_stft_mel_bwd")
+        _count(2)
+        return dwav, None, None, None, None, None, None
+
+
+def l1_sum(a, b, scale=1.0):
+    """scale * sum|a - b| -> 0-dim tensor (no autograd; feature-matching value, loss.py:249)."""
+    a, b = a.contiguous(), b.contiguous()
+    out = torch.empty((), device=a.device, dtype=torch.float32)
+    check(_lib.load().kt_l1_sum(ptr(a), ptr(b), a.numel(), float(scale), ptr(out), stream_ptr()), "kt_l1_sum")
+    _count(2)
+    return out

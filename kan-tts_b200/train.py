@@ -1,0 +1,166 @@
+"""The HiFi-GAN train step and its data-parallel gradient exchange.
+
+``GanStep.step`` follows ``GAN_Trainer.train_step`` (KAN-TTS kantts/train/trainer.py:469-589)
+statement for statement -- generator phase (mel + adversarial + feature-matching value), Adam,
+then the discriminator phase on a re-generated ``y_`` -- with two scheduling changes that do not
+alter any result:
+  * the discriminators' weight gradients of the GENERATOR phase are never computed nor reduced:
+    the reference computes, all-reduces and then zeroes them (trainer.py:577-578);
+  * losses are kept as device tensors; ``.item()`` is only called by ``losses_to_float``.
+
+Multi-GPU (one process per GPU, ``torch.distributed`` NCCL over NVLink/NVSwitch): the batch is
+sharded by utterance, replicas are identical, and the only exchange is the gradient all-reduce
+(mean) -- replacing the three DistributedDataParallel wrappers of kantts/models/__init__.py:71-84.
+Gradients of each model live in one flat fp32 buffer (``.grad`` tensors are views into it), so the
+exchange is ONE in-place NCCL all-reduce per model per phase with no packing copies.
+"""
+import torch
+import torch.distributed as dist
+
+
+class FlatGrads:
+    """Owns a flat fp32 gradient buffer for a module; every parameter's ``.grad`` is a view."""
+
+    def __init__(self, module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def all_reduce_mean(self, group=None):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.div_(dist.get_world_size(group))
+
+    def set_requires_grad(self, flag):
+        for p in self.params:
+            p.requires_grad_(flag)
+
+
+class GanStep:
+    """model = {"generator": G, "discriminator": {name: D}}, optimizer / scheduler dicts of the same
+    shape and ``criterion`` as built by the reference's builders (or this package's)."""
+
+    def __init__(self, model, optimizer, scheduler, criterion, config, skip_unused_d_grads=True):
+        self.model, self.optimizer, self.scheduler = model, optimizer, scheduler
+        self.criterion, self.config = criterion, config
+        self.skip_unused_d_grads = skip_unused_d_grads
+        self.g_grads = FlatGrads(model["generator"])
+        self.d_grads = {k: FlatGrads(m) for k, m in model["discriminator"].items()}
+        self.steps = 1
+
+    def step(self, batch):
+        """batch = (y (B,1,T) waveform, x (B,80,T/hop) mel) already on the device -> dict of loss tensors"""
+        y, x = batch
+        cfg, crit, model = self.config, self.criterion, self.model
+        log = {}
+        if self.steps >= cfg.get("generator_train_start_steps", 0):
+            y_ = model["generator"](x)
+            gen_loss = 0.0
+            if crit.get("stft_loss", None):
+                sc_loss, mag_loss = crit["stft_loss"](y_, y)
+                gen_loss = gen_loss + (sc_loss + mag_loss) * crit["stft_loss"].weights
+                log["spectral_convergence_loss"], log["log_stft_magnitude_loss"] = sc_loss, mag_loss
+            if crit.get("mel_loss", None):
+                mel_loss = crit["mel_loss"](y_, y)
+                gen_loss = gen_loss + mel_loss * crit["mel_loss"].weights
+                log["mel_loss"] = mel_loss
+            if self.steps > cfg["discriminator_train_start_steps"]:
+                if self.skip_unused_d_grads:
+                    for fg in self.d_grads.values():
+                        fg.set_requires_grad(False)
+                adv_loss = 0.0
+                fmap_lst_ = []
+                for name, disc in model["discriminator"].items():
+                    p_, fmap_ = disc(y_)
+                    fmap_lst_.append(fmap_)
+                    adv_loss = adv_loss + crit["generator_adv_loss"](p_)
+                gen_loss = gen_loss + adv_loss * crit["generator_adv_loss"].weights
+                log["adversarial_loss"] = adv_loss
+                if crit.get("feat_match_loss", None):
+                    fmap_lst = []
+                    for name, disc in model["discriminator"].items():
+                        with torch.no_grad():
+                            p, fmap = disc(y)
+                            fmap_lst.append(fmap)
+                    fm_loss = 0.0
+                    for fmap_, fmap in zip(fmap_lst, fmap_lst_):          # argument order: trainer.py:535-538
+                        fm_loss = fm_loss + crit["feat_match_loss"](fmap_, fmap)
+                    log["feature_matching_loss"] = fm_loss
+                    gen_loss = gen_loss + fm_loss * crit["feat_match_loss"].weights
+                if self.skip_unused_d_grads:
+                    for fg in self.d_grads.values():
+                        fg.set_requires_grad(True)
+            log["generator_loss"] = gen_loss
+            self.g_grads.zero()
+            gen_loss.backward()
+            self.g_grads.all_reduce_mean()
+            if cfg["generator_grad_norm"] > 0:
+                torch.nn.utils.clip_grad_norm_(model["generator"].parameters(), cfg["generator_grad_norm"])
+            self.optimizer["generator"].step()
+            self.scheduler["generator"].step()
+
+        if self.steps > cfg["discriminator_train_start_steps"]:
+            with torch.no_grad():
+                y_ = model["generator"](x)
+            dis_loss = 0.0
+            real_t, fake_t = 0.0, 0.0
+            for name, disc in model["discriminator"].items():
+                p, fmap = disc(y)
+                p_, fmap_ = disc(y_.detach())
+                real_loss, fake_loss = crit["discriminator_adv_loss"](p_, p)
+                dis_loss = dis_loss + real_loss + fake_loss
+                real_t, fake_t = real_t + real_loss, fake_t + fake_loss
+            log["real_loss"], log["fake_loss"], log["discriminator_loss"] = real_t, fake_t, dis_loss
+            for fg in self.d_grads.values():
+                fg.zero()
+            dis_loss.backward()
+            for fg in self.d_grads.values():
+                fg.all_reduce_mean()
+            if cfg["discriminator_grad_norm"] > 0:
+                for m in model["discriminator"].values():
+                    torch.nn.utils.clip_grad_norm_(m.parameters(), cfg["discriminator_grad_norm"])
+            for key in self.optimizer["discriminator"].keys():
+                self.optimizer["discriminator"][key].step()
+            for key in self.scheduler["discriminator"].keys():
+                self.scheduler["discriminator"][key].step()
+        self.steps += 1
+        return log
+
+
+def losses_to_float(log):
+    return {k: (float(v) if torch.is_tensor(v) else v) for k, v in log.items()}
+
+
+def optimizer_builder(model_params, opt_name, opt_params):
+    """kantts/models/__init__.py:16-19"""
+    return getattr(torch.optim, opt_name)(model_params, **opt_params)
+
+
+def hifigan_model_builder(config, device):
+    """kantts/models/__init__.py:28-86 without the DDP wrappers (GanStep reduces the flat gradient
+    buffers itself); scheduler = torch MultiStepLR as in the shipped yamls."""
+    from . import hifigan
+    model = {"discriminator": {}}
+    optimizer = {"discriminator": {}}
+    scheduler = {"discriminator": {}}
+    for name, sect in config["Model"].items():
+        if name == "Generator":
+            m = hifigan.Generator(**sect["params"]).to(device)
+        else:
+            m = getattr(hifigan, name)(**sect["params"]).to(device)
+        opt = optimizer_builder(m.parameters(), sect["optimizer"].get("type", "Adam"), sect["optimizer"].get("params", {}))
+        sch_t = sect["scheduler"].get("type", "StepLR")
+        sch = getattr(torch.optim.lr_scheduler, sch_t)(opt, **sect["scheduler"].get("params", {}))
+        if name == "Generator":
+            model["generator"], optimizer["generator"], scheduler["generator"] = m, opt, sch
+        else:
+            model["discriminator"][name], optimizer["discriminator"][name], scheduler["discriminator"][name] = m, opt, sch
+    return model, optimizer, scheduler
