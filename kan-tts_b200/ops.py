@@ -27,6 +27,67 @@ def _count(n=1):
     _launches += n
 
 
+class _Profiler:
+    """Optional per-call CUDA-event timing (bench.py's roofline leg): each instrumented library call
+    is bracketed by two events on the launching stream and tagged with its algorithmic work."""
+
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, flops, nbytes in self.records:
+            d = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            d["calls"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["bytes"] += nbytes
+        return out
+
+
+_profiler = None
+
+
+def set_profiler(enabled):
+    """-> the active _Profiler (or None).  Timing adds host overhead: never on during a timed run."""
+    global _profiler
+    _profiler = _Profiler() if enabled else None
+    return _profiler
+
+
+class _timed:
+    __slots__ = ("name", "flops", "nbytes", "e0")
+
+    def __init__(self, name, flops=0.0, nbytes=0.0):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
+
+    def __enter__(self):
+        if _profiler is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _profiler is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _profiler.records.append((self.name, self.e0, e1, self.flops, self.nbytes))
+        return False
+
+
+def _conv_work(spec, d):
+    """(algorithmic FLOPs, layer-boundary HBM bytes) of one pass over the layer."""
+    rows_out = d.batch * d.nsub * d.t_out
+    rows_in = d.batch * d.nsub * d.t_in
+    if spec.transposed:
+        macs = rows_in * spec.kernel * spec.c_in * spec.c_out
+    else:
+        macs = rows_out * spec.kernel * (spec.c_in // spec.groups) * spec.c_out
+    nbytes = 4.0 * (rows_in * spec.c_in + rows_out * spec.c_out + spec.w_numel)
+    return 2.0 * macs, nbytes
+
+
 @dataclass
 class ConvSpec:
     """Static description of one conv layer (forward semantics), see KtConv1dDesc."""
@@ -176,14 +237,18 @@ class ConvFn(torch.autograd.Function):
             assert resid.shape == y.shape, (resid.shape, y.shape)
         bd = None if bias is None else bias.detach()
         nt = _tc_tile(lib, spec, d, 0)
+        flops, nbytes = _conv_work(spec, d)
         if nt:
             global _tc_launches
-            check(lib.kt_conv1d_fwd_tc(ctypes.byref(d), ptr(x), ptr(pw.tc_image(spec, 0, nt)), ptr(bd), ptr(resid),
-                                       ptr(y), stream_ptr()), "kt_conv1d_fwd_tc")
+            img = pw.tc_image(spec, 0, nt)
+            with _timed("conv_fwd_tc", flops, nbytes):
+                check(lib.kt_conv1d_fwd_tc(ctypes.byref(d), ptr(x), ptr(img), ptr(bd), ptr(resid),
+                                           ptr(y), stream_ptr()), "kt_conv1d_fwd_tc")
             _tc_launches += spec.stride if spec.transposed else 1
         else:
-            check(lib.kt_conv1d_fwd(ctypes.byref(d), ptr(x), ptr(pw.w_fwd), ptr(bd), ptr(resid), ptr(y), stream_ptr()),
-                  "kt_conv1d_fwd")
+            with _timed("conv_fwd_ffma", flops, nbytes):
+                check(lib.kt_conv1d_fwd(ctypes.byref(d), ptr(x), ptr(pw.w_fwd), ptr(bd), ptr(resid), ptr(y),
+                                        stream_ptr()), "kt_conv1d_fwd")
         _count(spec.stride if spec.transposed else 1)
         ctx.spec, ctx.d = spec, d
         ctx.w_bwd, ctx.norm = pw.w_bwd, pw.norm
@@ -204,14 +269,17 @@ class ConvFn(torch.autograd.Function):
         dx = dres = dbias = dv = dg = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
+            flops, nbytes = _conv_work(spec, d)
             if ctx.nt_bwd:
                 global _tc_launches
-                check(lib.kt_conv1d_bwd_data_tc(ctypes.byref(d), ptr(dy), ptr(y), ptr(ctx.img_bwd), ptr(x), ptr(dx), st),
-                      "kt_conv1d_bwd_data_tc")
+                with _timed("conv_dgrad_tc", flops, nbytes):
+                    check(lib.kt_conv1d_bwd_data_tc(ctypes.byref(d), ptr(dy), ptr(y), ptr(ctx.img_bwd), ptr(x),
+                                                    ptr(dx), st), "kt_conv1d_bwd_data_tc")
                 _tc_launches += 1
             else:
-                check(lib.kt_conv1d_bwd_data(ctypes.byref(d), ptr(dy), ptr(y), ptr(ctx.w_bwd), ptr(x), ptr(dx), st),
-                      "kt_conv1d_bwd_data")
+                with _timed("conv_dgrad_ffma", flops, nbytes):
+                    check(lib.kt_conv1d_bwd_data(ctypes.byref(d), ptr(dy), ptr(y), ptr(ctx.w_bwd), ptr(x), ptr(dx),
+                                                 st), "kt_conv1d_bwd_data")
             _count(max(spec.stride if not spec.transposed else 1, spec.upsample))
         if ctx.has_resid and ctx.needs_input_grad[1]:
             dres = dy
@@ -221,8 +289,10 @@ class ConvFn(torch.autograd.Function):
             dw = torch.empty(spec.w_numel, device=x.device, dtype=torch.float32)
             if need_b:
                 dbias = torch.empty(spec.c_out, device=x.device, dtype=torch.float32)
-            check(lib.kt_conv1d_bwd_weight(ctypes.byref(d), ptr(x), ptr(dy), ptr(y), ptr(dw), ptr(dbias), st),
-                  "kt_conv1d_bwd_weight")
+            flops, nbytes = _conv_work(spec, d)
+            with _timed("conv_wgrad_ffma", flops, nbytes):
+                check(lib.kt_conv1d_bwd_weight(ctypes.byref(d), ptr(x), ptr(dy), ptr(y), ptr(dw), ptr(dbias), st),
+                      "kt_conv1d_bwd_weight")
             _count(4 if need_b else 2)
             if need_w:
                 vd = v.detach().contiguous()

@@ -1,0 +1,292 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Every check goes through the C ABI
+(ctypes -> libkantts_b200.so) and compares against the CPU oracle / golden vectors from the
+unmodified reference.  Tolerances (north_star): waveform RMS <= 1e-3, mel-L1 <= 1e-4; we hold the
+exact-fp32 (FFMA) kernels to ~1e-5 relative and the tcgen05 bf16x3 kernels to 1e-4 relative."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import kantts_b200 as K
+from kantts_b200 import ops
+from kantts_b200._lib import KT_ACT_LRELU, KT_ACT_TANH
+from conftest import rel_l2
+from oracle import convref
+from oracle import hifigan as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _to_rows(x):           # (B, C, T) -> (B, T, C) ; (B, C, H, P) -> (B, H, P, C)
+    return x.permute(0, 2, 1).contiguous() if x.dim() == 3 else x.permute(0, 2, 3, 1).contiguous()
+
+
+def _from_rows(x):
+    return x.permute(0, 2, 1) if x.dim() == 3 else x.permute(0, 3, 1, 2)
+
+
+CASES = {
+    # name: (spec kwargs, B, T, period, use_resid, weight_norm)
+    "causal_dilated_resid": (dict(c_in=64, c_out=64, kernel=7, dilation=3, pad_left=18, act_in=0.1), 2, 300, 0, True, True),
+    "noncausal_k3": (dict(c_in=32, c_out=32, kernel=3, pad_left=1, pad_right=1, act_in=0.1), 2, 257, 0, True, True),
+    "msd_grouped_strided": (dict(c_in=32, c_out=64, kernel=41, stride=4, pad_left=20, pad_right=20, groups=4, act_out=0.1), 2, 512, 0, False, True),
+    "msd_grouped16": (dict(c_in=128, c_out=256, kernel=41, stride=4, pad_left=20, pad_right=20, groups=16, act_out=0.1), 2, 300, 0, False, True),
+    "cin1_k15": (dict(c_in=1, c_out=16, kernel=15, pad_left=7, pad_right=7, act_out=0.1), 3, 1000, 0, False, True),
+    "cout1_tanh": (dict(c_in=32, c_out=1, kernel=7, pad_left=6, act_in=0.01, act_out="tanh"), 2, 500, 0, False, True),
+    "cin2_cout1_aux": (dict(c_in=2, c_out=1, kernel=15, pad_left=7, pad_right=7, act_out=0.1), 2, 700, 0, False, True),
+    "deconv_causal": (dict(c_in=64, c_out=32, kernel=16, stride=8, transposed=True, crop=8, act_in=0.1), 2, 40, 0, True, True),
+    "deconv_odd_noncausal": (dict(c_in=32, c_out=16, kernel=11, stride=5, pad_left=3, transposed=True, act_in=0.1), 2, 33, 0, True, True),
+    "deconv_k4s2": (dict(c_in=128, c_out=64, kernel=4, stride=2, transposed=True, crop=2, act_in=0.1), 2, 150, 0, True, True),
+    "upsample_conv": (dict(c_in=64, c_out=32, kernel=7, pad_left=6, upsample=8, act_in=0.1), 2, 37, 0, False, True),
+    "upsample3_noncausal": (dict(c_in=16, c_out=8, kernel=7, pad_left=3, pad_right=3, upsample=3, act_in=0.1), 2, 50, 0, False, True),
+    "period_strided": (dict(c_in=4, c_out=8, kernel=5, stride=3, pad_left=2, pad_right=2, act_out=0.1), 2, 100, 3, False, True),
+    "period_cin1": (dict(c_in=1, c_out=32, kernel=5, stride=3, pad_left=2, pad_right=2, act_out=0.1), 2, 200, 7, False, True),
+    "period_post_plain": (dict(c_in=32, c_out=1, kernel=2, pad_left=1, pad_right=1), 2, 52, 5, False, False),
+    "period_stride1_tc": (dict(c_in=64, c_out=64, kernel=5, pad_left=2, pad_right=2, act_out=0.1), 2, 51, 5, False, True),
+    "tc_128_k11_d5": (dict(c_in=128, c_out=128, kernel=11, dilation=5, pad_left=50, act_in=0.1), 2, 1000, 0, True, True),
+    "tc_256_k3": (dict(c_in=256, c_out=256, kernel=3, pad_left=2, act_in=0.1), 2, 256, 0, True, True),
+    "tc_64_to_192": (dict(c_in=64, c_out=192, kernel=7, dilation=1, pad_left=3, pad_right=3), 1, 200, 0, False, True),
+    "tc_512_to_1024_k5": (dict(c_in=512, c_out=1024, kernel=5, pad_left=2, pad_right=2, act_out=0.1), 1, 140, 0, False, True),
+    "tc_deconv_256_128": (dict(c_in=256, c_out=128, kernel=16, stride=8, transposed=True, crop=8, act_in=0.1), 2, 32, 0, True, True),
+}
+
+
+def _run_case(name, force_ffma):
+    kw, B, T, period, use_resid, wn = CASES[name]
+    kw = dict(kw)
+    act_in = kw.pop("act_in", None)
+    act_out = kw.pop("act_out", None)
+    spec = ops.ConvSpec(**kw)
+    if act_in is not None:
+        spec.act_in, spec.act_in_slope = KT_ACT_LRELU, act_in
+    if act_out == "tanh":
+        spec.act_out = KT_ACT_TANH
+    elif act_out is not None:
+        spec.act_out, spec.act_out_slope = KT_ACT_LRELU, act_out
+    g = torch.Generator().manual_seed(hash(name) % 10000)
+    wshape = (spec.c_in, spec.c_out, spec.kernel) if spec.transposed else (spec.c_out, spec.c_in // spec.groups, spec.kernel)
+    v = torch.randn(wshape, generator=g) * 0.3
+    gg = (v.norm(2, dim=(1, 2), keepdim=True) * (1 + 0.2 * torch.randn(wshape[0], 1, 1, generator=g))) if wn else None
+    bias = 0.1 * torch.randn(spec.c_out, generator=g)
+    xs = (B, spec.c_in, T, period) if period else (B, spec.c_in, T)
+    x = torch.randn(xs, generator=g)
+    t_out = spec.t_out(T)
+    ys = (B, spec.c_out, t_out, period) if period else (B, spec.c_out, t_out)
+    resid = torch.randn(ys, generator=g) if use_resid else None
+    r = torch.randn(ys, generator=g)
+
+    # oracle (CPU)
+    xo, vo, bo = x.clone().requires_grad_(True), v.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    go = gg.clone().requires_grad_(True) if wn else None
+    ro = resid.clone().requires_grad_(True) if use_resid else None
+    w = O.weight_norm_weight(go, vo) if wn else vo
+    yo = convref.conv_layer(xo, w, bo, ro, stride=spec.stride, dilation=spec.dilation, pad_left=spec.pad_left,
+                            pad_right=spec.pad_right, groups=spec.groups, transposed=spec.transposed,
+                            upsample=spec.upsample, crop=spec.crop, act_in=act_in, act_out=act_out)
+    assert tuple(yo.shape) == ys, (yo.shape, ys)
+    (yo * r).sum().backward()
+
+    # product (GPU, through the C ABI)
+    ops.set_force_ffma(force_ffma)
+    try:
+        xg = _to_rows(x).to(DEV).requires_grad_(True)
+        vg, bg = v.to(DEV).requires_grad_(True), bias.to(DEV).requires_grad_(True)
+        g2 = gg.to(DEV).requires_grad_(True) if wn else None
+        rg = _to_rows(resid).to(DEV).requires_grad_(True) if use_resid else None
+        tc0 = ops.tc_launch_count()
+        y = ops.conv(xg, spec, ops.PreparedWeight(), vg, g2, bg, rg)
+        (y * _to_rows(r).to(DEV)).sum().backward()
+        used_tc = ops.tc_launch_count() > tc0
+    finally:
+        ops.set_force_ffma(False)
+    tol = 1e-4 if used_tc else 2e-5
+    assert rel_l2(_from_rows(y).cpu(), yo) < tol, ("y", rel_l2(_from_rows(y).cpu(), yo))
+    assert rel_l2(_from_rows(xg.grad).cpu(), xo.grad) < tol, ("dx", rel_l2(_from_rows(xg.grad).cpu(), xo.grad))
+    assert rel_l2(vg.grad.cpu(), vo.grad) < 5e-5, ("dv", rel_l2(vg.grad.cpu(), vo.grad))
+    assert rel_l2(bg.grad.cpu(), bo.grad) < 5e-5, "dbias"
+    if wn:
+        assert rel_l2(g2.grad.cpu(), go.grad) < 5e-5, "dg"
+    if use_resid:
+        assert rel_l2(_from_rows(rg.grad).cpu(), ro.grad) < 1e-6, "dresid"
+    return used_tc
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_conv_layer_ffma_vs_oracle(name):
+    _run_case(name, force_ffma=True)
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if n.startswith("tc_") or n.endswith("_tc") or n in ("causal_dilated_resid", "deconv_k4s2")])
+def test_conv_layer_tcgen05_vs_oracle(name):
+    assert _run_case(name, force_ffma=False), "expected the tcgen05 path to be taken"
+
+
+def _load(module, sd):
+    module.load_state_dict(sd, strict=True)
+    return module.to(DEV)
+
+
+@pytest.mark.parametrize("name", ["gen_small_causal", "gen_small_noncausal"])
+@pytest.mark.parametrize("force_ffma", [True, False])
+def test_generator_matches_reference_golden(golden, name, force_ffma):
+    g = golden(name)
+    ops.set_force_ffma(force_ffma)
+    try:
+        m = _load(K.Generator(**g.cfg), g.group("sd/"))
+        x = g.t("x").to(DEV).requires_grad_(True)
+        y = m(x)
+        ref = g.t("y")
+        assert y.shape == ref.shape
+        rms = float((y.detach().cpu() - ref).pow(2).mean().sqrt())
+        assert rms < (1e-5 if force_ffma else 1e-4), rms
+        (y * g.t("r").to(DEV)).sum().backward()
+    finally:
+        ops.set_force_ffma(False)
+    tol = 1e-4 if force_ffma else 5e-4
+    assert rel_l2(x.grad.cpu(), g.t("grad_x")) < tol
+    refg = g.group("grad/")
+    worst = max((rel_l2(p.grad.cpu(), refg[k]), k) for k, p in m.named_parameters())
+    assert worst[0] < tol, worst
+
+
+@pytest.mark.parametrize("name,cls", [("mpd_small", "MultiPeriodDiscriminator"), ("msd_small", "MultiScaleDiscriminator")])
+def test_discriminators_match_reference_golden(golden, name, cls):
+    g = golden(name)
+    m = _load(getattr(K, cls)(**g.cfg), g.group("sd/"))
+    m.train()
+    y = g.t("y").to(DEV).requires_grad_(True)
+    outs, fmaps = m(y)
+    loss = 0.0
+    for i, o in enumerate(outs):
+        assert o.shape == g.t(f"out{i}").shape
+        assert float((o.detach().cpu() - g.t(f"out{i}")).abs().max()) < 2e-5
+        for l, f in enumerate(fmaps[i]):
+            assert f.shape == g.t(f"fmap{i}_{l}").shape
+            assert rel_l2(f.detach().cpu(), g.t(f"fmap{i}_{l}")) < 2e-5
+        loss = loss + (o * g.t(f"r{i}").to(DEV)).sum()
+    loss.backward()
+    assert rel_l2(y.grad.cpu(), g.t("grad_y")) < 1e-4
+    refg = g.group("grad/")
+    worst = max((rel_l2(p.grad.cpu(), refg[k]), k) for k, p in m.named_parameters())
+    assert worst[0] < 2e-4, worst
+    sd = m.state_dict()
+    for k, v in g.group("after/").items():
+        assert rel_l2(sd[k].cpu(), v) < 1e-5, k
+
+
+def test_mel_and_stft_losses_match_reference_golden(golden):
+    g = golden("mel_stft")
+    y = g.t("y").to(DEV)
+    cfgs = {"default": {}, "yaml24k": dict(fs=24000, fft_size=1024, hop_size=240, win_length=1024, fmin=0, fmax=8000, log_base=None),
+            "c2": dict(fs=22050, fft_size=1024, hop_size=256, win_length=1024, fmin=0, fmax=8000)}
+    for tag, cfg in cfgs.items():
+        mel = K.MelSpectrogram(**cfg).to(DEV)(y)
+        ref = g.t(f"mel_{tag}")
+        assert mel.shape == ref.shape
+        assert float((mel.cpu() - ref).abs().mean()) < 1e-4          # mel-L1 tolerance of the north star
+        y_hat = g.t("y_hat").to(DEV).requires_grad_(True)
+        loss = K.MelSpectrogramLoss(**cfg).to(DEV)(y_hat, y)
+        assert abs(float(loss) - float(g.t(f"loss_{tag}"))) < 1e-4
+        loss.backward()
+        assert rel_l2(y_hat.grad.cpu(), g.t(f"grad_{tag}")) < 5e-3
+    y_hat = g.t("y_hat").to(DEV).requires_grad_(True)
+    sc, mag = K.MultiResolutionSTFTLoss().to(DEV)(y_hat, y)
+    assert abs(float(sc) - float(g.t("stft_sc"))) < 1e-4
+    assert abs(float(mag) - float(g.t("stft_mag"))) < 1e-4
+    (sc + mag).backward()
+    assert rel_l2(y_hat.grad.cpu(), g.t("stft_grad")) < 5e-3
+
+
+def _small_config(g):
+    adam = {"type": "Adam", "params": {"lr": 2e-4, "betas": [0.5, 0.9], "weight_decay": 0.0}}
+    sched = {"type": "MultiStepLR", "params": {"gamma": 0.5, "milestones": [200000]}}
+    return {"Model": {"Generator": {"params": g.cfg["generator"], "optimizer": adam, "scheduler": sched},
+                      "MultiScaleDiscriminator": {"params": g.cfg["msd"], "optimizer": adam, "scheduler": sched},
+                      "MultiPeriodDiscriminator": {"params": g.cfg["mpd"], "optimizer": adam, "scheduler": sched}},
+            "Loss": g.cfg["loss"], "generator_train_start_steps": 1, "discriminator_train_start_steps": 0,
+            "generator_grad_norm": -1, "discriminator_grad_norm": -1}
+
+
+@pytest.mark.parametrize("force_ffma", [True, False])
+def test_gan_train_step_matches_reference_trainer(golden, force_ffma):
+    """One full GAN step (both phases, Adam) vs the unmodified GAN_Trainer.train_step."""
+    g = golden("trainstep_small")
+    cfg = _small_config(g)
+    ops.set_force_ffma(force_ffma)
+    try:
+        torch.manual_seed(0)
+        model, opt, sched = K.hifigan_model_builder(cfg, DEV)
+        model["generator"].load_state_dict(g.group("before/g/"))
+        model["discriminator"]["MultiScaleDiscriminator"].load_state_dict(g.group("before/msd/"))
+        model["discriminator"]["MultiPeriodDiscriminator"].load_state_dict(g.group("before/mpd/"))
+        crit = K.criterion_builder(cfg, DEV)
+        step = K.GanStep(model, opt, sched, crit, cfg)
+        log = K.train.losses_to_float(step.step((g.t("y").to(DEV), g.t("x").to(DEV))))
+    finally:
+        ops.set_force_ffma(False)
+    for k in ("mel_loss", "feature_matching_loss", "generator_loss", "real_loss", "fake_loss", "discriminator_loss"):
+        ref = float(g.arrays["loss/" + k])
+        assert abs(log[k] - ref) <= 2e-4 * max(1.0, abs(ref)), (k, log[k], ref)
+    for tag, m in (("g", model["generator"]), ("msd", model["discriminator"]["MultiScaleDiscriminator"]),
+                   ("mpd", model["discriminator"]["MultiPeriodDiscriminator"])):
+        after, before = g.group(f"after/{tag}/"), g.group(f"before/{tag}/")
+        sd = m.state_dict()
+        num = den = 0.0
+        for k, v in after.items():
+            num += float(((sd[k].cpu() - v).double() ** 2).sum())
+            den += float(((before[k] - v).double() ** 2).sum())
+        assert num <= 2e-2 * den, (tag, num, den)      # Adam's first step is lr*sign-like: loose on purpose
+
+
+def test_c1_full_generator_matches_reference(golden):
+    """BASELINE config 1: class-default Generator (seed 1234) forward, (1,80,32) -> (1,1,8192)."""
+    g = golden("c1_generator")
+    torch.manual_seed(1234)
+    m = K.Generator().to(DEV).eval()
+    x = g.t("x").to(DEV)
+    ref = g.t("y")
+    for force in (True, False):
+        ops.set_force_ffma(force)
+        try:
+            with torch.no_grad():
+                y = m(x).cpu()
+        finally:
+            ops.set_force_ffma(False)
+        rms = float((y - ref).pow(2).mean().sqrt())
+        assert rms < 1e-3, (force, rms)                               # waveform RMS tolerance
+        mel_l1 = float((O.mel_spectrogram(y) - O.mel_spectrogram(ref)).abs().mean())
+        assert mel_l1 < 1e-4, (force, mel_l1)                         # mel-L1 tolerance
+
+
+def test_full_size_properties():
+    """Size-independent properties at the C2 shapes (B=16, 8192 samples)."""
+    torch.manual_seed(3)
+    B, T = 16, 8192
+    # DWT: orthonormal analysis -> energy preserved; adjoint test <Ax, y> = <x, A^T y>
+    x = torch.randn(B, T, device=DEV, requires_grad=True)
+    y = ops.DwtFn.apply(x)
+    assert y.shape == (B, (T + 5) // 2, 2)
+    assert abs(float(y.pow(2).sum() / x.pow(2).sum()) - 1) < 1e-5
+    r = torch.randn_like(y)
+    (y * r).sum().backward()
+    x2 = torch.randn(B, T, device=DEV)
+    assert abs(float((ops.DwtFn.apply(x2) * r).sum()) - float((x2 * x.grad).sum())) < 1e-2 * float(r.norm() * x2.norm()) * 1e-3 + 1e-2
+    # conv linearity + adjointness on the heaviest resblock shape (C=128, T=2048, k=11, d=5), tcgen05 path
+    spec = ops.ConvSpec(c_in=128, c_out=128, kernel=11, dilation=5, pad_left=50)
+    v = torch.randn(128, 128, 11, device=DEV) * 0.05
+    cache = ops.PreparedWeight()
+    a = torch.randn(B, 2048, 128, device=DEV, requires_grad=True)
+    b = torch.randn(B, 2048, 128, device=DEV)
+    ya, yb, yab = ops.conv(a, spec, cache, v), ops.conv(b, spec, cache, v), ops.conv(a + 2 * b, spec, cache, v)
+    assert rel_l2(yab, ya + 2 * yb) < 1e-4
+    rr = torch.randn_like(ya)
+    (ya * rr).sum().backward()
+    lhs = float((ops.conv(b, spec, cache, v) * rr).sum())
+    rhs = float((b * a.grad).sum())
+    assert abs(lhs - rhs) < 2e-4 * float(rr.norm() * yb.norm())
+    # mel of a full batch: bounded to [-4, 4], silence maps to the floor
+    mel = K.MelSpectrogram().to(DEV)
+    out = mel(torch.zeros(B, 1, T, device=DEV))
+    assert out.shape == (B, 80, 33) and float(out.max()) == -4.0
