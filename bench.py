@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="profiling mode: 1 warm-up + K steps, nothing else (not a bench number)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -224,6 +225,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.ncu:
+        step.step((y_d, x_d))
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for _ in range(args.steps):
+            step.step((y_d, x_d))
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"ncu_mode": True, "steps": args.steps, "launches": ops.launch_count()}))
+        return
     for _ in range(W):
         log = step.step((y_d, x_d))
     barrier()

@@ -56,6 +56,7 @@ __device__ __forceinline__ float side_apply(float v, float aux, int mode, float 
 }
 
 constexpr int kMaxTaps = 64;
+constexpr int kMaxDynSmem = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
 
 // One "phase" of a generalised 1-D convolution (see conv_ffma.cu for the decomposition):
 //   out[bb][o_off + o_step*m][co] (+)= epi( sum_n sum_ci W[tap_j[n]][ci][co] * in[bb][ floor((m*i_step + tap_ioff[n]) / up) ][ci] )

@@ -10,7 +10,7 @@
 //              applying the fused pre-activation / output-activation derivative, split it into the hi /
 //              lo bf16 planes and store them as SWIZZLE_128B shared-memory images (rows = time steps).
 //              im2col-free: tap j of the conv is the SAME image read through a UMMA descriptor whose
-//              start address is shifted by tap_ioff[j] rows (matrix-base-offset re-phases the swizzle).
+//              start address is shifted by tap_ioff[j] rows (the 128-byte swizzle is a function of absolute smem address bits, so a row shift needs no re-phasing).
 //   warp 4     streams the pre-swizzled bf16 weight tiles (hi + lo, one tap x 64 input channels) with
 //              cp.async.bulk (TMA engine) into a ring of shared-memory stages, mbarrier complete_tx.
 //   warp 5     one elected thread issues tcgen05.mma (M=128, N=NT, K=16) x 4 k-slices x 3 products per
@@ -18,6 +18,7 @@
 //   warps 0-3  epilogue: tcgen05.ld the fp32 accumulators (thread = output row), bias / activation /
 //              residual (or act' mask for the data gradient), 16-byte stores to the channels-last output.
 #include <algorithm>
+#include <atomic>
 #include <vector>
 
 #include "common.cuh"
@@ -333,10 +334,10 @@ static int run_tc(TcParams p, cudaStream_t st) {
   p.nb_stages = std::min(6, budget / b_stage);
   KT_REQUIRE(p.nb_stages >= 2, "conv_tc: shared memory budget exceeded (rows=%d NT=%d)", p.rows, p.NT);
   const size_t smem = 1024 + a_bytes + (size_t)p.nb_stages * b_stage + 256;
-  static thread_local bool cfg = false;
-  if (!cfg) {
-    KT_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    cfg = true;
+  static std::atomic<bool> cfg{false};
+  if (!cfg.load(std::memory_order_acquire)) {
+    KT_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    cfg.store(true, std::memory_order_release);
   }
   dim3 grid(ceil_div(ph.M, kTcM), p.ntiles, p.batch);
   conv_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
@@ -355,8 +356,11 @@ static Side make_side_tc(const float* p, const float* aux, int act, float slope,
 static int tc_flags() {
   static int flags = -1;
   if (flags < 0) {
+    // Measured on B200 (round 1, profiles/r01_notes.md): the SWIZZLE_128B XOR is applied to ABSOLUTE
+    // shared-memory address bits, so a row-shifted descriptor needs matrix-base-offset = 0; setting it
+    // to (addr >> 7) & 7 double-applies the phase and gives wrong results.  Env override kept for the record.
     const char* e = getenv("KT_TC_BASE_OFFSET");
-    flags = (e && e[0] == '0') ? 0 : 1;
+    flags = (e && e[0] == '1') ? 1 : 0;
   }
   return flags;
 }

@@ -171,7 +171,7 @@ int stft_mel_fwd(const KtMelDesc* d, const float* wav, const float* window, cons
   if (rc) return rc;
   KT_REQUIRE(wav && window && (!mel || melmat), "stft_mel_fwd: null argument");
   const size_t smem = (2 * (size_t)p.n_fft + p.n_fft / 2 + 1) * sizeof(float);
-  static thread_local bool cfg = false;
+  static bool cfg = false;
   if (!cfg) { KT_CHECK_CUDA(cudaFuncSetAttribute(stft_mel_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); cfg = true; }
   stft_mel_fwd_kernel<<<p.batch * p.frames, 256, smem, st>>>(p, wav, window, melmat, mel, amp, spec);
   KT_CHECK_CUDA(cudaGetLastError());
@@ -186,7 +186,7 @@ int stft_mel_bwd(const KtMelDesc* d, const float* dmel, const float* damp, const
   KT_REQUIRE(spec && window && dwav && (dmel || damp) && (!dmel || melmat), "stft_mel_bwd: null argument");
   KT_CHECK_CUDA(cudaMemsetAsync(dwav, 0, (size_t)p.batch * p.t * sizeof(float), st));
   const size_t smem = (2 * (size_t)p.n_fft + p.n_fft / 2 + 1 + p.n_mels) * sizeof(float);
-  static thread_local bool cfg = false;
+  static bool cfg = false;
   if (!cfg) { KT_CHECK_CUDA(cudaFuncSetAttribute(stft_mel_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); cfg = true; }
   stft_mel_bwd_kernel<<<p.batch * p.frames, 256, smem, st>>>(p, dmel, damp, spec, window, melmat, dwav);
   KT_CHECK_CUDA(cudaGetLastError());

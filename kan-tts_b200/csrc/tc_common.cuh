@@ -110,8 +110,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // K-major operand  (rows = M/N index, K contiguous):  SBO = 1024 (8 rows), LBO unused (1)
 // MN-major operand (rows = K index, M/N contiguous):  SBO = 1024 (8 K-rows), LBO = stride between
 //                                                     64-element M/N groups
-// `base_offset` = (start >> 7) & 7 re-phases the swizzle pattern when the start address is not
-// 1024-byte aligned -- this is what lets a conv tap be a plain ROW SHIFT of one staged image.
+// The swizzle XOR acts on absolute shared-memory address bits [4,7) ^= [7,10) (measured on B200), so a
+// start address advanced by whole 128-byte rows reads a ROW-SHIFTED view of the same staged image --
+// this is what makes a conv tap a descriptor offset.  `use_base_offset` (matrix base offset =
+// (start >> 7) & 7) must stay false for that; it is kept only to document the failed variant.
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t start_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
                                                     bool use_base_offset) {
   uint64_t d = 0;

@@ -33,6 +33,9 @@ CASES = {
     "noncausal_k3": (dict(c_in=32, c_out=32, kernel=3, pad_left=1, pad_right=1, act_in=0.1), 2, 257, 0, True, True),
     "msd_grouped_strided": (dict(c_in=32, c_out=64, kernel=41, stride=4, pad_left=20, pad_right=20, groups=4, act_out=0.1), 2, 512, 0, False, True),
     "msd_grouped16": (dict(c_in=128, c_out=256, kernel=41, stride=4, pad_left=20, pad_right=20, groups=16, act_out=0.1), 2, 300, 0, False, True),
+    "msd_tiny_groups_a": (dict(c_in=16, c_out=16, kernel=41, stride=4, pad_left=20, pad_right=20, groups=4, act_out=0.1), 2, 2048, 0, False, True),
+    "msd_tiny_groups_b": (dict(c_in=16, c_out=32, kernel=41, stride=4, pad_left=20, pad_right=20, groups=16, act_out=0.1), 2, 512, 0, False, True),
+    "msd_tiny_groups_c": (dict(c_in=64, c_out=64, kernel=41, stride=1, pad_left=20, pad_right=20, groups=16, act_out=0.1), 2, 40, 0, False, False),
     "cin1_k15": (dict(c_in=1, c_out=16, kernel=15, pad_left=7, pad_right=7, act_out=0.1), 3, 1000, 0, False, True),
     "cout1_tanh": (dict(c_in=32, c_out=1, kernel=7, pad_left=6, act_in=0.01, act_out="tanh"), 2, 500, 0, False, True),
     "cin2_cout1_aux": (dict(c_in=2, c_out=1, kernel=15, pad_left=7, pad_right=7, act_out=0.1), 2, 700, 0, False, True),
