@@ -129,6 +129,13 @@ int kt_conv1d_fwd_tc(const KtConv1dDesc* d, const float* x, const void* wimg, co
 int kt_conv1d_bwd_data_tc(const KtConv1dDesc* d, const float* dy, const float* y, const void* wimg, const float* x,
                           float* dx, void* stream);
 
+/* tcgen05 weight gradient (time is the contraction dimension; split-K partial tiles go to `workspace`,
+ * a second kernel reduces them).  kt_conv1d_bwd_weight_tc_workspace: floats of workspace the layer
+ * needs, 0 when the layer is not supported (then use kt_conv1d_bwd_weight).  dw / dbias as above. */
+int64_t kt_conv1d_bwd_weight_tc_workspace(const KtConv1dDesc* d);
+int kt_conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy, const float* y, float* dw,
+                            float* dbias, float* workspace, int64_t workspace_floats, void* stream);
+
 /* Elementwise pieces of Generator.forward (hifigan.py:157 `x = sin(x) + x`). */
 int kt_sinadd_fwd(const float* x, float* y, int64_t n, void* stream);
 int kt_sinadd_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream);

@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkantts_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "conv_ffma.cu", "conv_tc.cu", "weights.cu", "misc.cu", "stft_mel.cu"]
+SOURCES = ["api.cu", "conv_ffma.cu", "conv_tc.cu", "wgrad_tc.cu", "weights.cu", "misc.cu", "stft_mel.cu"]
 
 KT_ACT_NONE, KT_ACT_LRELU, KT_ACT_TANH = 0, 1, 2
 KT_PATH_AUTO, KT_PATH_FFMA, KT_PATH_TC = 0, 1, 2
@@ -58,6 +58,8 @@ PROTOTYPES = {
     "kt_weight_pack_tc": [_P, _I, _I, _I, _I, _P, _P],
     "kt_conv1d_fwd_tc": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P],
     "kt_conv1d_bwd_data_tc": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P],
+    "kt_conv1d_bwd_weight_tc_workspace": [ctypes.POINTER(KtConv1dDesc)],
+    "kt_conv1d_bwd_weight_tc": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P, _L, _P],
     "kt_version": [],
     "kt_has_tc": [],
 }
@@ -101,7 +103,7 @@ def load():
     for name, argtypes in PROTOTYPES.items():
         fn = getattr(lib, name)            # AttributeError here = header / library mismatch
         fn.argtypes = argtypes
-        fn.restype = ctypes.c_int
+        fn.restype = ctypes.c_int64 if name.endswith("_workspace") else ctypes.c_int
     lib.kt_last_error.argtypes = []
     lib.kt_last_error.restype = ctypes.c_char_p
     _lib = lib

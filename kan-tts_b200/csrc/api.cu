@@ -17,6 +17,8 @@ int dwt_bwd(const float*, float*, int, int, cudaStream_t);
 int l1_sum(const float*, const float*, long long, float, float*, cudaStream_t);
 int stft_mel_fwd(const KtMelDesc*, const float*, const float*, const float*, float*, float*, float*, cudaStream_t);
 int stft_mel_bwd(const KtMelDesc*, const float*, const float*, const float*, const float*, const float*, float*, cudaStream_t);
+long long wgrad_tc_workspace(const KtConv1dDesc*);
+int conv1d_bwd_weight_tc(const KtConv1dDesc*, const float*, const float*, const float*, float*, float*, float*, long long, cudaStream_t);
 int tc_plan(const KtConv1dDesc*, int);
 int tc_pack_weights(const float*, int, int, int, int, void*, cudaStream_t);
 int conv1d_fwd_tc(const KtConv1dDesc*, const float*, const void*, const float*, const float*, float*, cudaStream_t);
@@ -102,6 +104,17 @@ int kt_conv1d_fwd_tc(const KtConv1dDesc* d, const float* x, const void* wimg, co
   if (rc) return rc;
   KT_REQUIRE(x && wimg && y, "kt_conv1d_fwd_tc: null pointer");
   return kt::conv1d_fwd_tc(d, x, wimg, bias, resid, y, ST(stream));
+}
+int64_t kt_conv1d_bwd_weight_tc_workspace(const KtConv1dDesc* d) {
+  if (kt::validate_conv(d)) return 0;
+  return kt::wgrad_tc_workspace(d);
+}
+int kt_conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy, const float* y, float* dw,
+                            float* dbias, float* workspace, int64_t workspace_floats, void* stream) {
+  int rc = kt::validate_conv(d);
+  if (rc) return rc;
+  KT_REQUIRE(x && dy && dw, "kt_conv1d_bwd_weight_tc: null pointer");
+  return kt::conv1d_bwd_weight_tc(d, x, dy, y, dw, dbias, workspace, workspace_floats, ST(stream));
 }
 int kt_conv1d_bwd_data_tc(const KtConv1dDesc* d, const float* dy, const float* y, const void* wimg, const float* x,
                           float* dx, void* stream) {

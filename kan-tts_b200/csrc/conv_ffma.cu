@@ -690,6 +690,14 @@ int conv1d_bwd_weight_ffma(const KtConv1dDesc* d, const float* x, const float* d
   return KT_OK;
 }
 
+int colsum_bias(const Side& s, long long rows, int c, float* out, cudaStream_t st) {
+  KT_CHECK_CUDA(cudaMemsetAsync(out, 0, (size_t)c * sizeof(float), st));
+  dim3 grid(ceil_div(c, 32), (unsigned)std::min<long long>(std::max<long long>(1, rows / 256), 512));
+  colsum_kernel<<<grid, 256, 0, st>>>(s, rows, c, out);
+  KT_CHECK_CUDA(cudaGetLastError());
+  return KT_OK;
+}
+
 int validate_conv(const KtConv1dDesc* d) { return validate(d); }
 
 }  // namespace kt

@@ -1,0 +1,351 @@
+// tcgen05 weight-gradient kernel (bf16x3 split precision, fp32 accumulation in TMEM).
+//
+//   dW[tap j][ca][cb] = sum_{batch, m}  fa(A[b][m + ioff_j][ca]) * fb(Bm[b][m][cb])
+//   conv layer:  A = act_in(x) (rows = input time, channels ca = C_in),  Bm = dy * act_out'(y) (C_out)
+//
+// The contraction runs over TIME, so both MMA operands are "MN-major" views of the same kind of
+// shared-memory image the forward kernel uses ([time rows][64 channels] bf16, SWIZZLE_128B):
+// K = 16 consecutive rows per tcgen05.mma, M / N = channels (64-element groups, LBO apart).
+// A conv tap is again a pure descriptor row shift of the staged A image.  Two ways to fill M = 128:
+//   mode 0 (C_in >= 128): two 64-channel images of one tap (LBO = image stride)
+//   mode 1 (C_in == 64) : ONE image, two taps: LBO = (ioff_{j+1} - ioff_j) * 128 bytes
+// Each CTA owns (ca tile, cb tile, a group of U "units" = U*NT TMEM columns <= 512) for a slice of the
+// (batch, time) range (split-K); partial tiles go to a workspace with plain 16-byte stores and a
+// second kernel reduces over the splits (cheaper than ~10^7 fp32 atomics per launch).
+#include <algorithm>
+#include <atomic>
+#include <vector>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace kt {
+
+using namespace tc;
+
+constexpr int kWgTK = 64;        // time rows per staged chunk
+constexpr int kWgThreads = 192;
+constexpr int kWgMaxUnits = 8;
+
+struct WgTcParams {
+  Side a, b;
+  float* ws;
+  int batch, t_a, t_b, ca, cb, taps_total;
+  int M;                       // base rows per batch item
+  int mode, NT, n_cb_tiles, n_ca_tiles;
+  int units_total, units_per_cta;
+  int nsplit, chunks_per_batch;
+  int a_groups, b_groups;      // 64-channel images per stage on each side
+  int rows_a;                  // A image rows (TK + halo, multiple of 8)
+  int tmem_cols;
+  int ntaps;
+  int tap_j[kMaxTaps];
+  int tap_ioff[kMaxTaps];      // ascending
+};
+
+__device__ __forceinline__ void stage_rows(uint8_t* img_hi, uint8_t* img_lo, const Side& s, const float* base,
+                                           const float* aux_base, int c_total, int ch0, int t0, int t_valid_lo,
+                                           int t_valid_hi, int rows, int tid) {
+  // 128 threads: thread -> (row = tid/8 + 16*i, 16-byte chunk q = tid%8 of the 64-channel row)
+  const int q = tid & 7;
+  for (int r = tid >> 3; r < rows; r += 16) {
+    const int t = t0 + r;
+    float x[8];
+    if (t >= t_valid_lo && t < t_valid_hi) {
+      const long long off = (long long)t * c_total + ch0 + q * 8;
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(base + off));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(base + off + 4));
+      x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
+      if (s.mode == SIDE_LRELU) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = x[e] > 0.f ? x[e] : x[e] * s.slope;
+      } else if (s.mode >= SIDE_DLRELU) {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(aux_base + off));
+        const float4 a1 = __ldg(reinterpret_cast<const float4*>(aux_base + off + 4));
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = side_apply(x[e], a[e], s.mode, s.slope);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = 0.f;
+    }
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    const uint32_t o = sw128_offset((uint32_t)r, (uint32_t)q);
+    *reinterpret_cast<uint4*>(img_hi + o) = hi;
+    *reinterpret_cast<uint4*>(img_lo + o) = lo;
+  }
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int img_a = p.rows_a * 128;            // one plane of one A image
+  const int img_b = kWgTK * 128;               // one plane of one B image
+  const int stage_bytes = 2 * (p.a_groups * img_a + p.b_groups * img_b);
+  uint8_t* stage0 = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * (size_t)stage_bytes);
+  uint64_t* full = bars;        // [2] producers -> MMA
+  uint64_t* empty = bars + 2;   // [2] MMA -> producers
+  uint64_t* tmem_full = bars + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ca_tile = blockIdx.x / p.n_cb_tiles;
+  const int cb_tile = blockIdx.x % p.n_cb_tiles;
+  const int u0 = blockIdx.y * p.units_per_cta;
+  const int nu = min(p.units_per_cta, p.units_total - u0);
+  const int split = blockIdx.z;
+
+  // taps covered by this CTA and their row-offset range
+  const int taps_per_unit = p.mode == 1 ? 2 : 1;
+  const int n_first = u0 * taps_per_unit;
+  const int n_last = min((u0 + nu) * taps_per_unit, p.ntaps) - 1;
+  const int gmin = p.tap_ioff[n_first];
+  const int gmax = p.tap_ioff[n_last];
+
+  const long long units = (long long)p.batch * p.chunks_per_batch;
+  const long long c_begin = units * split / p.nsplit;
+  const long long c_end = units * (split + 1) / p.nsplit;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+    fence_proxy_async();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== producers =====================
+    int it = 0;
+    for (long long c = c_begin; c < c_end; ++c, ++it) {
+      const int s = it & 1;
+      mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
+      const int bb = (int)(c / p.chunks_per_batch);
+      const int m0 = (int)(c % p.chunks_per_batch) * kWgTK;
+      uint8_t* st = stage0 + (size_t)s * stage_bytes;
+      const float* a_base = p.a.p + (long long)bb * p.t_a * p.ca;
+      const float* a_aux = p.a.aux ? p.a.aux + (long long)bb * p.t_a * p.ca : nullptr;
+      const float* b_base = p.b.p + (long long)bb * p.t_b * p.cb;
+      const float* b_aux = p.b.aux ? p.b.aux + (long long)bb * p.t_b * p.cb : nullptr;
+      // A images: rows t = m0 + gmin + r.  Rows whose base row m = t - ioff would be >= M only meet
+      // zero B rows, so plain [0, t_a) validity is enough.
+      for (int g = 0; g < p.a_groups; ++g) {
+        uint8_t* hi = st + (size_t)g * 2 * img_a;
+        stage_rows(hi, hi + img_a, p.a, a_base, a_aux, p.ca, ca_tile * (p.mode == 0 ? 128 : 64) + g * 64, m0 + gmin, 0,
+                   p.t_a, p.rows_a, tid);
+      }
+      uint8_t* bst = st + (size_t)p.a_groups * 2 * img_a;
+      for (int g = 0; g < p.b_groups; ++g) {
+        uint8_t* hi = bst + (size_t)g * 2 * img_b;
+        stage_rows(hi, hi + img_b, p.b, b_base, b_aux, p.cb, cb_tile * p.NT + g * 64, m0, 0, min(p.M, p.t_b), kWgTK, tid);
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[s]);
+    }
+
+    // ===================== epilogue: TMEM -> workspace partial tiles =====================
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;  // M index inside the unit
+    const uint32_t t_lane = tmem_acc + ((uint32_t)(warp * 32) << 16);
+    for (int u = 0; u < nu; ++u) {
+      int tap_n, ca_idx;
+      if (p.mode == 0) { tap_n = u0 + u; ca_idx = ca_tile * 128 + row; }
+      else { tap_n = (u0 + u) * 2 + (row >> 6); ca_idx = row & 63; }
+      const bool valid = tap_n < p.ntaps;
+      const long long obase = valid ? (((long long)split * p.taps_total + p.tap_j[tap_n]) * p.ca + ca_idx) * p.cb + (long long)cb_tile * p.NT : 0;
+      for (int n0 = 0; n0 < p.NT; n0 += 32) {
+        uint32_t rr[32];
+        tmem_ld32(t_lane + (uint32_t)(u * p.NT + n0), rr);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            *reinterpret_cast<float4*>(p.ws + obase + n0 + e) =
+                make_float4(__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.NT, 1, 1);
+      const uint32_t lbo_b = 2u * (uint32_t)img_b;
+      int it = 0;
+      for (long long c = c_begin; c < c_end; ++c, ++it) {
+        const int s = it & 1;
+        mbar_wait(&full[s], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t st = smem_u32(stage0 + (size_t)s * stage_bytes);
+        const uint32_t b_hi = st + (uint32_t)(p.a_groups * 2 * img_a);
+        const uint32_t b_lo = b_hi + (uint32_t)img_b;
+        for (int u = 0; u < nu; ++u) {
+          int n_a;
+          uint32_t lbo_a;
+          if (p.mode == 0) {
+            n_a = u0 + u;
+            lbo_a = 2u * (uint32_t)img_a;
+          } else {
+            n_a = (u0 + u) * 2;
+            const int n_b2 = min(n_a + 1, p.ntaps - 1);
+            lbo_a = (uint32_t)(p.tap_ioff[n_b2] - p.tap_ioff[n_a]) * 128u;
+            if (lbo_a == 0) lbo_a = 128u;  // odd tap count: rows 64..127 of the last unit are discarded
+          }
+          const uint32_t shift = (uint32_t)(p.tap_ioff[n_a] - gmin) * 128u;
+          const uint32_t a_hi = st + shift;
+          const uint32_t a_lo = a_hi + (uint32_t)img_a;
+          const uint32_t d = tmem_acc + (uint32_t)(u * p.NT);
+#pragma unroll
+          for (int ks = 0; ks < kWgTK / 16; ++ks) {
+            const uint32_t ko = (uint32_t)ks * 16u * 128u;
+            const uint64_t da_hi = smem_desc_sw128(a_hi + ko, lbo_a, 1024, false);
+            const uint64_t da_lo = smem_desc_sw128(a_lo + ko, lbo_a, 1024, false);
+            const uint64_t db_hi = smem_desc_sw128(b_hi + ko, lbo_b, 1024, false);
+            const uint64_t db_lo = smem_desc_sw128(b_lo + ko, lbo_b, 1024, false);
+            const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+            umma_bf16(d, da_lo, db_hi, idesc, acc);
+            umma_bf16(d, da_hi, db_lo, idesc, 1);
+            umma_bf16(d, da_hi, db_hi, idesc, 1);
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+    __syncwarp();
+  }
+
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
+  }
+}
+
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n, int nsplit) {
+  const long long n4 = n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 acc = __ldg(reinterpret_cast<const float4*>(ws) + i);
+    for (int s = 1; s < nsplit; ++s) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ws + (long long)s * n) + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(dw)[i] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------
+struct WgPlan {
+  bool ok;
+  WgTcParams p;
+  size_t smem;
+  long long ws_floats;
+};
+
+std::vector<Phase> conv_phases(const KtConv1dDesc* d, int dir);
+
+static WgPlan make_plan(const KtConv1dDesc* d0) {
+  WgPlan pl{};
+  pl.ok = false;
+  if (d0->transposed || d0->groups != 1 || d0->upsample != 1 || d0->stride != 1) return pl;
+  KtConv1dDesc d = *d0;
+  if (d.nsub > 1) {  // stride-1 period conv folds to dilation * nsub (see conv_tc.cu)
+    d.t_in *= d.nsub; d.t_out *= d.nsub; d.dilation *= d.nsub; d.pad_left *= d.nsub; d.nsub = 1;
+  }
+  const int ca = d.c_in, cb = d.c_out;
+  if (ca % 64 != 0 || cb % 64 != 0) return pl;
+  if (ca != 64 && ca % 128 != 0) return pl;
+  WgTcParams& p = pl.p;
+  p.batch = d.batch; p.t_a = d.t_in; p.t_b = d.t_out; p.ca = ca; p.cb = cb; p.taps_total = d.kernel;
+  p.M = d.t_out;
+  p.ntaps = d.kernel;
+  for (int j = 0; j < d.kernel; ++j) { p.tap_j[j] = j; p.tap_ioff[j] = j * d.dilation - d.pad_left; }
+  p.mode = ca == 64 ? 1 : 0;
+  p.NT = cb % 256 == 0 ? 256 : (cb % 128 == 0 ? 128 : 64);
+  if (cb < p.NT) p.NT = cb;
+  p.n_cb_tiles = cb / p.NT;
+  p.n_ca_tiles = p.mode == 0 ? ca / 128 : 1;
+  p.units_total = p.mode == 0 ? p.ntaps : (p.ntaps + 1) / 2;
+  p.a_groups = p.mode == 0 ? 2 : 1;
+  p.b_groups = p.NT / 64;
+  // shared memory: 2 stages of (A images with halo + B images); shrink units per CTA until it fits
+  int U = std::min({kWgMaxUnits, 512 / p.NT, p.units_total});
+  for (; U >= 1; --U) {
+    const int taps_per_unit = p.mode == 1 ? 2 : 1;
+    const int span_taps = std::min(U * taps_per_unit, p.ntaps);
+    const int halo = (span_taps - 1) * d.dilation;
+    const int rows_a = (kWgTK + halo + 7) & ~7;
+    const size_t stage = 2 * ((size_t)p.a_groups * rows_a * 128 + (size_t)p.b_groups * kWgTK * 128);
+    const size_t smem = 1024 + 2 * stage + 128;
+    if (smem <= (size_t)kMaxDynSmem) {
+      p.units_per_cta = U; p.rows_a = rows_a; pl.smem = smem;
+      break;
+    }
+  }
+  if (U < 1) return pl;
+  p.tmem_cols = 32;
+  while (p.tmem_cols < p.units_per_cta * p.NT) p.tmem_cols <<= 1;
+  if (p.tmem_cols > 512) return pl;
+  p.chunks_per_batch = ceil_div(p.M, kWgTK);
+  const long long units = (long long)p.batch * p.chunks_per_batch;
+  const long long base = (long long)p.n_ca_tiles * p.n_cb_tiles * ceil_div(p.units_total, p.units_per_cta);
+  long long nsplit = std::max<long long>(1, (148 + base - 1) / base);
+  nsplit = std::min(nsplit, units);
+  p.nsplit = (int)nsplit;
+  pl.ws_floats = nsplit * (long long)p.taps_total * ca * cb;
+  pl.ok = true;
+  return pl;
+}
+
+// floats of workspace needed by conv1d_bwd_weight_tc (0 = layer not supported)
+long long wgrad_tc_workspace(const KtConv1dDesc* d) {
+  const WgPlan pl = make_plan(d);
+  return pl.ok ? pl.ws_floats : 0;
+}
+
+int colsum_bias(const Side& s, long long rows, int c, float* out, cudaStream_t st);  // conv_ffma.cu
+
+int conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy, const float* y, float* dw,
+                         float* dbias, float* ws, long long ws_floats, cudaStream_t st) {
+  WgPlan pl = make_plan(d);
+  KT_REQUIRE(pl.ok, "conv1d_bwd_weight_tc: layer not supported by the tcgen05 path");
+  KT_REQUIRE(ws && ws_floats >= pl.ws_floats, "conv1d_bwd_weight_tc: workspace too small (%lld < %lld floats)", ws_floats, pl.ws_floats);
+  KT_REQUIRE(d->act_out == KT_ACT_NONE || y != nullptr, "bwd_weight: y required when act_out != NONE");
+  WgTcParams& p = pl.p;
+  p.a = Side{x, nullptr, d->act_in == KT_ACT_LRELU ? SIDE_LRELU : SIDE_PLAIN, d->act_in_slope};
+  p.b = Side{dy, y, SIDE_PLAIN, d->act_out_slope};
+  if (d->act_out == KT_ACT_LRELU) p.b.mode = SIDE_DLRELU;
+  else if (d->act_out == KT_ACT_TANH) p.b.mode = SIDE_DTANH;
+  else p.b.aux = nullptr;
+  p.ws = ws;
+  static std::atomic<bool> cfg{false};
+  if (!cfg.load(std::memory_order_acquire)) {
+    KT_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    cfg.store(true, std::memory_order_release);
+  }
+  dim3 grid(p.n_ca_tiles * p.n_cb_tiles, ceil_div(p.units_total, p.units_per_cta), p.nsplit);
+  wgrad_tc_kernel<<<grid, kWgThreads, pl.smem, st>>>(p);
+  KT_CHECK_CUDA(cudaGetLastError());
+  const long long n = (long long)p.taps_total * p.ca * p.cb;
+  const int blocks = (int)std::min<long long>((n / 4 + 255) / 256, 148LL * 8);
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dw, n, p.nsplit);
+  KT_CHECK_CUDA(cudaGetLastError());
+  if (dbias) {
+    const long long rows = (long long)d->batch * d->nsub * d->t_out;
+    int rc = colsum_bias(p.b, rows, d->c_out, dbias, st);
+    if (rc) return rc;
+  }
+  return KT_OK;
+}
+
+}  // namespace kt
