@@ -115,8 +115,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 
   if (warp < 4) {
     // ===================== activation producers =====================
-    const int q = tid & 7;        // 16-byte bf16 chunk (8 channels) of the 64-channel row
-    const int r_first = tid >> 3; // 0..15
     const float* in_b = p.in.p + (long long)bb * p.t_in * p.c_in;
     const float* aux_b = p.in.aux ? p.in.aux + (long long)bb * p.t_in * p.c_in : nullptr;
     for (int c = 0; c < p.kchunks; ++c) {
@@ -124,35 +122,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       mbar_wait(&empty_a[s], ((c >> 1) & 1) ^ 1);
       uint8_t* img_hi = a_base + s * a_stage_bytes;
       uint8_t* img_lo = img_hi + img_bytes;
-      const int ch = c * kTcKC + q * 8;
-      for (int r = r_first; r < p.rows; r += 16) {
-        const int t = row_lo + r;
-        float x[8];
-        if (t >= 0 && t < p.t_in) {
-          const long long off = (long long)t * p.c_in + ch;
-          const float4 v0 = __ldg(reinterpret_cast<const float4*>(in_b + off));
-          const float4 v1 = __ldg(reinterpret_cast<const float4*>(in_b + off + 4));
-          x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-          if (p.in.mode == SIDE_LRELU) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = x[e] > 0.f ? x[e] : x[e] * p.in.slope;
-          } else if (p.in.mode >= SIDE_DLRELU) {
-            const float4 a0 = __ldg(reinterpret_cast<const float4*>(aux_b + off));
-            const float4 a1 = __ldg(reinterpret_cast<const float4*>(aux_b + off + 4));
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = side_apply(x[e], a[e], p.in.mode, p.in.slope);
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) x[e] = 0.f;
-        }
-        uint4 hi, lo;
-        split8(x, hi, lo);
-        const uint32_t o = sw128_offset((uint32_t)r, (uint32_t)q);
-        *reinterpret_cast<uint4*>(img_hi + o) = hi;
-        *reinterpret_cast<uint4*>(img_lo + o) = lo;
-      }
+      stage_rows<5>(img_hi, img_lo, p.in, in_b, aux_b, p.c_in, c * kTcKC, row_lo, 0, p.t_in, p.rows, tid);
       fence_proxy_async();
       mbar_arrive(&full_a[s]);
     }

@@ -6,6 +6,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include "common.cuh"
+
 namespace kt {
 namespace tc {
 
@@ -152,4 +154,53 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
 }
 
 }  // namespace tc
+
+// Stage `rows` time steps x 64 channels of a channels-last fp32 tensor into a hi / lo bf16
+// SWIZZLE_128B image pair.  128 threads: thread -> (row = tid/8 + 16*i, 16-byte chunk q = tid%8).
+// Loads are issued in batches of NB rows per thread BEFORE any conversion so that each thread keeps
+// 2*NB (4*NB with an aux tensor) 16-byte loads in flight: with one 192-thread CTA per SM the
+// staging loop is otherwise pure DRAM/L2 latency.
+template <int NB>
+__device__ __forceinline__ void stage_rows(uint8_t* img_hi, uint8_t* img_lo, const Side& s, const float* base,
+                                           const float* aux_base, int c_total, int ch0, int t0, int t_valid_lo,
+                                           int t_valid_hi, int rows, int tid) {
+  const int q = tid & 7;
+  const bool has_aux = s.mode >= SIDE_DLRELU;
+  for (int r0 = tid >> 3; r0 < rows; r0 += 16 * NB) {
+    float4 v[NB][2], a[NB][2];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int r = r0 + 16 * i;
+      const int t = t0 + r;
+      const bool ok = r < rows && t >= t_valid_lo && t < t_valid_hi;
+      const long long off = ok ? (long long)t * c_total + ch0 + q * 8 : 0;
+      v[i][0] = ok ? __ldg(reinterpret_cast<const float4*>(base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[i][1] = ok ? __ldg(reinterpret_cast<const float4*>(base + off + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_aux) {
+        a[i][0] = ok ? __ldg(reinterpret_cast<const float4*>(aux_base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        a[i][1] = ok ? __ldg(reinterpret_cast<const float4*>(aux_base + off + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int r = r0 + 16 * i;
+      if (r >= rows) break;
+      float x[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
+      if (s.mode == SIDE_LRELU) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = x[e] > 0.f ? x[e] : x[e] * s.slope;
+      } else if (has_aux) {
+        const float ax[8] = {a[i][0].x, a[i][0].y, a[i][0].z, a[i][0].w, a[i][1].x, a[i][1].y, a[i][1].z, a[i][1].w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = side_apply(x[e], ax[e], s.mode, s.slope);
+      }
+      uint4 hi, lo;
+      tc::split8(x, hi, lo);
+      const uint32_t o = tc::sw128_offset((uint32_t)r, (uint32_t)q);
+      *reinterpret_cast<uint4*>(img_hi + o) = hi;
+      *reinterpret_cast<uint4*>(img_lo + o) = lo;
+    }
+  }
+}
+
 }  // namespace kt

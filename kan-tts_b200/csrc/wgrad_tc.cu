@@ -43,41 +43,6 @@ struct WgTcParams {
   int tap_ioff[kMaxTaps];      // ascending
 };
 
-__device__ __forceinline__ void stage_rows(uint8_t* img_hi, uint8_t* img_lo, const Side& s, const float* base,
-                                           const float* aux_base, int c_total, int ch0, int t0, int t_valid_lo,
-                                           int t_valid_hi, int rows, int tid) {
-  // 128 threads: thread -> (row = tid/8 + 16*i, 16-byte chunk q = tid%8 of the 64-channel row)
-  const int q = tid & 7;
-  for (int r = tid >> 3; r < rows; r += 16) {
-    const int t = t0 + r;
-    float x[8];
-    if (t >= t_valid_lo && t < t_valid_hi) {
-      const long long off = (long long)t * c_total + ch0 + q * 8;
-      const float4 v0 = __ldg(reinterpret_cast<const float4*>(base + off));
-      const float4 v1 = __ldg(reinterpret_cast<const float4*>(base + off + 4));
-      x[0] = v0.x; x[1] = v0.y; x[2] = v0.z; x[3] = v0.w; x[4] = v1.x; x[5] = v1.y; x[6] = v1.z; x[7] = v1.w;
-      if (s.mode == SIDE_LRELU) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) x[e] = x[e] > 0.f ? x[e] : x[e] * s.slope;
-      } else if (s.mode >= SIDE_DLRELU) {
-        const float4 a0 = __ldg(reinterpret_cast<const float4*>(aux_base + off));
-        const float4 a1 = __ldg(reinterpret_cast<const float4*>(aux_base + off + 4));
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) x[e] = side_apply(x[e], a[e], s.mode, s.slope);
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) x[e] = 0.f;
-    }
-    uint4 hi, lo;
-    split8(x, hi, lo);
-    const uint32_t o = sw128_offset((uint32_t)r, (uint32_t)q);
-    *reinterpret_cast<uint4*>(img_hi + o) = hi;
-    *reinterpret_cast<uint4*>(img_lo + o) = lo;
-  }
-}
-
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -138,13 +103,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       // zero B rows, so plain [0, t_a) validity is enough.
       for (int g = 0; g < p.a_groups; ++g) {
         uint8_t* hi = st + (size_t)g * 2 * img_a;
-        stage_rows(hi, hi + img_a, p.a, a_base, a_aux, p.ca, ca_tile * (p.mode == 0 ? 128 : 64) + g * 64, m0 + gmin, 0,
+        stage_rows<5>(hi, hi + img_a, p.a, a_base, a_aux, p.ca, ca_tile * (p.mode == 0 ? 128 : 64) + g * 64, m0 + gmin, 0,
                    p.t_a, p.rows_a, tid);
       }
       uint8_t* bst = st + (size_t)p.a_groups * 2 * img_a;
       for (int g = 0; g < p.b_groups; ++g) {
         uint8_t* hi = bst + (size_t)g * 2 * img_b;
-        stage_rows(hi, hi + img_b, p.b, b_base, b_aux, p.cb, cb_tile * p.NT + g * 64, m0, 0, min(p.M, p.t_b), kWgTK, tid);
+        stage_rows<4>(hi, hi + img_b, p.b, b_base, b_aux, p.cb, cb_tile * p.NT + g * 64, m0, 0, min(p.M, p.t_b), kWgTK, tid);
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);

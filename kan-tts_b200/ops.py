@@ -33,6 +33,18 @@ class _Profiler:
 
     def __init__(self):
         self.records = []
+        self.details = []
+
+    def by_layer(self):
+        """{(kernel class, layer signature): [calls, ms, flops]} -- development breakdown."""
+        torch.cuda.synchronize()
+        out = {}
+        for (name, e0, e1, flops, _), det in zip(self.records, self.details):
+            d = out.setdefault((name, det), [0, 0.0, 0.0])
+            d[0] += 1
+            d[1] += e0.elapsed_time(e1)
+            d[2] += flops
+        return out
 
     def summary(self):
         torch.cuda.synchronize()
@@ -56,11 +68,17 @@ def set_profiler(enabled):
     return _profiler
 
 
-class _timed:
-    __slots__ = ("name", "flops", "nbytes", "e0")
+def _sig(spec, d):
+    return (f"{spec.c_in}->{spec.c_out} k{spec.kernel} s{spec.stride} d{spec.dilation} g{spec.groups}"
+            f"{' T' if spec.transposed else ''}{f' up{spec.upsample}' if spec.upsample > 1 else ''}"
+            f" B{d.batch}x{d.nsub} t{d.t_in}")
 
-    def __init__(self, name, flops=0.0, nbytes=0.0):
-        self.name, self.flops, self.nbytes = name, flops, nbytes
+
+class _timed:
+    __slots__ = ("name", "flops", "nbytes", "e0", "detail")
+
+    def __init__(self, name, flops=0.0, nbytes=0.0, detail=""):
+        self.name, self.flops, self.nbytes, self.detail = name, flops, nbytes, detail
 
     def __enter__(self):
         if _profiler is not None:
@@ -73,6 +91,7 @@ class _timed:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             _profiler.records.append((self.name, self.e0, e1, self.flops, self.nbytes))
+            _profiler.details.append(self.detail)
         return False
 
 
@@ -205,6 +224,21 @@ def set_force_ffma(flag):
     _FORCE_FFMA = bool(flag)
 
 
+_WGRAD_TC = os.environ.get("KANTTS_B200_WGRAD_TC", "1") != "0"
+
+
+def _wgrad_tc_workspace(lib, spec, d):
+    """fp32 workspace floats for the tcgen05 weight-gradient kernel, 0 = use the FFMA kernel."""
+    if _FORCE_FFMA or not _WGRAD_TC or spec.path == KT_PATH_FFMA:
+        return 0
+    key = ("wg", d.batch, d.nsub, d.t_in)
+    n = spec._descs.get(key)
+    if n is None:
+        n = int(lib.kt_conv1d_bwd_weight_tc_workspace(ctypes.byref(d)))
+        spec._descs[key] = n
+    return n
+
+
 def _tc_tile(lib, spec, d, direction):
     if _FORCE_FFMA or spec.path == KT_PATH_FFMA:
         return 0
@@ -241,12 +275,12 @@ class ConvFn(torch.autograd.Function):
         if nt:
             global _tc_launches
             img = pw.tc_image(spec, 0, nt)
-            with _timed("conv_fwd_tc", flops, nbytes):
+            with _timed("conv_fwd_tc", flops, nbytes, _sig(spec, d)):
                 check(lib.kt_conv1d_fwd_tc(ctypes.byref(d), ptr(x), ptr(img), ptr(bd), ptr(resid),
                                            ptr(y), stream_ptr()), "kt_conv1d_fwd_tc")
             _tc_launches += spec.stride if spec.transposed else 1
         else:
-            with _timed("conv_fwd_ffma", flops, nbytes):
+            with _timed("conv_fwd_ffma", flops, nbytes, _sig(spec, d)):
                 check(lib.kt_conv1d_fwd(ctypes.byref(d), ptr(x), ptr(pw.w_fwd), ptr(bd), ptr(resid), ptr(y),
                                         stream_ptr()), "kt_conv1d_fwd")
         _count(spec.stride if spec.transposed else 1)
@@ -272,12 +306,12 @@ class ConvFn(torch.autograd.Function):
             flops, nbytes = _conv_work(spec, d)
             if ctx.nt_bwd:
                 global _tc_launches
-                with _timed("conv_dgrad_tc", flops, nbytes):
+                with _timed("conv_dgrad_tc", flops, nbytes, _sig(spec, d)):
                     check(lib.kt_conv1d_bwd_data_tc(ctypes.byref(d), ptr(dy), ptr(y), ptr(ctx.img_bwd), ptr(x),
                                                     ptr(dx), st), "kt_conv1d_bwd_data_tc")
                 _tc_launches += 1
             else:
-                with _timed("conv_dgrad_ffma", flops, nbytes):
+                with _timed("conv_dgrad_ffma", flops, nbytes, _sig(spec, d)):
                     check(lib.kt_conv1d_bwd_data(ctypes.byref(d), ptr(dy), ptr(y), ptr(ctx.w_bwd), ptr(x), ptr(dx),
                                                  st), "kt_conv1d_bwd_data")
             _count(max(spec.stride if not spec.transposed else 1, spec.upsample))
@@ -290,9 +324,17 @@ class ConvFn(torch.autograd.Function):
             if need_b:
                 dbias = torch.empty(spec.c_out, device=x.device, dtype=torch.float32)
             flops, nbytes = _conv_work(spec, d)
-            with _timed("conv_wgrad_ffma", flops, nbytes):
-                check(lib.kt_conv1d_bwd_weight(ctypes.byref(d), ptr(x), ptr(dy), ptr(y), ptr(dw), ptr(dbias), st),
-                      "kt_conv1d_bwd_weight")
+            ws_floats = _wgrad_tc_workspace(lib, spec, d)
+            if ws_floats:
+                ws = torch.empty(ws_floats, device=x.device, dtype=torch.float32)
+                with _timed("conv_wgrad_tc", flops, nbytes, _sig(spec, d)):
+                    check(lib.kt_conv1d_bwd_weight_tc(ctypes.byref(d), ptr(x), ptr(dy), ptr(y), ptr(dw), ptr(dbias),
+                                                      ptr(ws), ws_floats, st), "kt_conv1d_bwd_weight_tc")
+                _tc_launches += 1
+            else:
+                with _timed("conv_wgrad_ffma", flops, nbytes, _sig(spec, d)):
+                    check(lib.kt_conv1d_bwd_weight(ctypes.byref(d), ptr(x), ptr(dy), ptr(y), ptr(dw), ptr(dbias), st),
+                          "kt_conv1d_bwd_weight")
             _count(4 if need_b else 2)
             if need_w:
                 vd = v.detach().contiguous()
