@@ -23,7 +23,7 @@ def lib():
 
 def test_library_exports_every_declared_symbol(lib):
     header = open(os.path.join(ROOT, "include", "kantts_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|const char\*)\s+(kt_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(kt_\w+)\s*\(", header, flags=re.M))
     assert len(declared) >= 15
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in kantts_b200.h but not exported"
