@@ -5,12 +5,15 @@
 // ~2^-18 relative).  A single-pass TF32/BF16 MMA does not meet the path's tolerance (mel-L1 <= 1e-4,
 // SURVEY.md "hard parts"); three bf16 MMAs do, at twice the rate of 3xTF32.
 //
-// Data flow per CTA (one 128-row output tile x NT output channels, one batch item):
-//   warps 0-3  stage the channels-last fp32 activation tile (128 + halo rows x 64 channels per K chunk),
-//              applying the fused pre-activation / output-activation derivative, split it into the hi /
-//              lo bf16 planes and store them as SWIZZLE_128B shared-memory images (rows = time steps).
-//              im2col-free: tap j of the conv is the SAME image read through a UMMA descriptor whose
-//              start address is shifted by tap_ioff[j] rows (the 128-byte swizzle is a function of absolute smem address bits, so a row shift needs no re-phasing).
+// Tile = 128 consecutive FLATTENED outputs (time m, sub-sequence w) of one batch item x NT channels.
+// Data flow per CTA:
+//   warps 0-3  stage the channels-last fp32 activation rows (fused pre-activation / activation
+//              derivative), split them into hi / lo bf16 planes and store SWIZZLE_128B shared-memory
+//              images (rows = flattened (time, sub-sequence) positions of ONE input residue class).
+//              im2col-free: tap j = residue image rho_j read through a UMMA descriptor whose start
+//              address is shifted by q_j * nsub rows (the 128-byte swizzle is a function of absolute
+//              smem address bits, so a row shift needs no re-phasing).  Stride s convs stage s residue
+//              images per 64-channel chunk; the period discriminator's (k,1) Conv2d needs nothing extra.
 //   warp 4     streams the pre-swizzled bf16 weight tiles (hi + lo, one tap x 64 input channels) with
 //              cp.async.bulk (TMA engine) into a ring of shared-memory stages, mbarrier complete_tx.
 //   warp 5     one elected thread issues tcgen05.mma (M=128, N=NT, K=16) x 4 k-slices x 3 products per
@@ -31,6 +34,7 @@ using namespace tc;
 constexpr int kTcM = 128;        // output rows per CTA
 constexpr int kTcKC = 64;        // input channels per K chunk (one 128-byte swizzle row of bf16)
 constexpr int kTcMaxRows = 256;  // image rows (128 + halo) upper bound
+constexpr int kTcMaxGroups = 8;  // residue classes (= input step) per phase
 
 // ---------------------------------------------------------------------------------------------
 // weight packing: fp32 W[taps][K][N] (kernel layout of conv_ffma.cu) -> bf16 hi/lo SWIZZLE_128B tiles
@@ -66,12 +70,19 @@ struct TcParams {
   const float* resid;
   Side mask;
   float* out;
-  int batch, t_in, t_out, c_in, c_out;
+  int batch, nsub, t_in, t_out, c_in, c_out;
   int out_act;
   float out_slope;
   int NT, ntiles, kchunks, rows, nb_stages, tmem_cols;
-  int flags;  // bit0: use matrix base offset
-  Phase ph;
+  // phase: out[(o_off + o_step*m), w] = sum_n W[tap_j[n]] in[(m + q_n)*i_step + rho_n, w]
+  int M, o_off, o_step, i_step, up, accumulate;
+  int ngroups;                        // residue classes actually used
+  int grp_rho[kTcMaxGroups];
+  int grp_qlo[kTcMaxGroups];
+  int grp_first[kTcMaxGroups + 1];    // taps of group g: [grp_first[g], grp_first[g+1])
+  int ntaps;
+  int tap_j[kMaxTaps];                // weight tap index, ordered by group
+  int tap_shift[kMaxTaps];            // image row shift (q_n - q_lo) * nsub
 };
 
 constexpr int kTcThreads = 192;
@@ -94,11 +105,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const Phase& ph = p.ph;
-  const int m0 = blockIdx.x * kTcM;
+  const int f0 = blockIdx.x * kTcM;   // first flattened output (m * nsub + w) of this tile
   const int nt = blockIdx.y;
   const int bb = blockIdx.z;
-  const int row_lo = m0 + ph.min_ioff;  // input time index of image row 0 (i_step == 1)
+  const int F = p.M * p.nsub;         // flattened outputs per batch item in this phase
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(&full_a[s], 128); mbar_init(&empty_a[s], 1); }
@@ -115,25 +125,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 
   if (warp < 4) {
     // ===================== activation producers =====================
-    const float* in_b = p.in.p + (long long)bb * p.t_in * p.c_in;
-    const float* aux_b = p.in.aux ? p.in.aux + (long long)bb * p.t_in * p.c_in : nullptr;
+    int it = 0;
     for (int c = 0; c < p.kchunks; ++c) {
-      const int s = c & 1;
-      mbar_wait(&empty_a[s], ((c >> 1) & 1) ^ 1);
-      uint8_t* img_hi = a_base + s * a_stage_bytes;
-      uint8_t* img_lo = img_hi + img_bytes;
-      stage_rows<5>(img_hi, img_lo, p.in, in_b, aux_b, p.c_in, c * kTcKC, row_lo, 0, p.t_in, p.rows, tid);
-      fence_proxy_async();
-      mbar_arrive(&full_a[s]);
+      for (int g = 0; g < p.ngroups; ++g, ++it) {
+        const int s = it & 1;
+        mbar_wait(&empty_a[s], ((it >> 1) & 1) ^ 1);
+        uint8_t* img_hi = a_base + s * a_stage_bytes;
+        RowMap rm;
+        rm.base_row = (long long)bb * p.t_in * p.nsub;
+        rm.fv0 = f0 + p.grp_qlo[g] * p.nsub;
+        rm.nsub = p.nsub; rm.step = p.i_step; rm.rho = p.grp_rho[g]; rm.up = p.up; rm.t_lim = p.t_in * p.up;
+        stage_rows<5>(img_hi, img_hi + img_bytes, p.in, p.in.p, p.in.aux, p.c_in, c * kTcKC, rm, p.rows, tid);
+        fence_proxy_async();
+        mbar_arrive(&full_a[s]);
+      }
     }
 
     // ===================== epilogue =====================
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    const int m = m0 + warp * 32 + lane;
-    const bool valid = m < ph.M;
-    const int to = ph.o_off + ph.o_step * (valid ? m : 0);
-    const long long obase = ((long long)bb * p.t_out + to) * p.c_out + (long long)nt * p.NT;
+    const int f = f0 + warp * 32 + lane;
+    const bool valid = f < F;
+    const int m = valid ? (p.nsub == 1 ? f : f / p.nsub) : 0;
+    const int w = valid ? f - m * p.nsub : 0;
+    const int to = p.o_off + p.o_step * m;
+    const long long obase = (((long long)bb * p.t_out + to) * p.nsub + w) * p.c_out + (long long)nt * p.NT;
     const uint32_t t_lane = tmem_acc + ((uint32_t)(warp * 32) << 16);
     for (int n0 = 0; n0 < p.NT; n0 += 32) {
       uint32_t rr[32];
@@ -173,7 +189,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             const float4 a = __ldg(reinterpret_cast<const float4*>(p.resid + o));
             v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
           }
-          if (ph.accumulate) {
+          if (p.accumulate) {
             const float4 a = *reinterpret_cast<const float4*>(p.out + o);
             v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
           }
@@ -187,11 +203,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     if (lane == 0) {
       int it = 0;
       for (int c = 0; c < p.kchunks; ++c) {
-        for (int n = 0; n < ph.ntaps; ++n, ++it) {
+        for (int n = 0; n < p.ntaps; ++n, ++it) {  // taps are ordered by group: same order as the MMA issuer
           const int s = it % p.nb_stages;
           const uint32_t par = ((it / p.nb_stages) & 1) ^ 1;
           mbar_wait(&empty_b[s], par);
-          const long long block = ((long long)ph.tap_j[n] * p.kchunks + c) * p.ntiles + nt;
+          const long long block = ((long long)p.tap_j[n] * p.kchunks + c) * p.ntiles + nt;
           const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + block * (long long)b_stage_bytes;
           mbar_arrive_expect_tx(&full_b[s], (uint32_t)b_stage_bytes);
           bulk_g2s(b_base + (size_t)s * b_stage_bytes, src, (uint32_t)b_stage_bytes, &full_b[s]);
@@ -203,37 +219,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_bf16(kTcM, p.NT, 0, 0);
-      const bool use_bo = (p.flags & 1) != 0;
-      int it = 0;
+      int it_a = 0, it_b = 0;
       uint32_t acc = 0;
       for (int c = 0; c < p.kchunks; ++c) {
-        const int sa = c & 1;
-        mbar_wait(&full_a[sa], (c >> 1) & 1);
-        tc_fence_after();
-        const uint32_t a_hi = smem_u32(a_base + sa * a_stage_bytes);
-        const uint32_t a_lo = a_hi + (uint32_t)img_bytes;
-        for (int n = 0; n < ph.ntaps; ++n, ++it) {
-          const int sb = it % p.nb_stages;
-          mbar_wait(&full_b[sb], (it / p.nb_stages) & 1);
+        for (int g = 0; g < p.ngroups; ++g, ++it_a) {
+          const int sa = it_a & 1;
+          mbar_wait(&full_a[sa], (it_a >> 1) & 1);
           tc_fence_after();
-          const uint32_t b_hi = smem_u32(b_base + (size_t)sb * b_stage_bytes);
-          const uint32_t b_lo = b_hi + (uint32_t)(p.NT * 128);
-          const uint32_t shift = (uint32_t)(ph.tap_ioff[n] - ph.min_ioff) * 128u;
+          const uint32_t a_hi = smem_u32(a_base + sa * a_stage_bytes);
+          const uint32_t a_lo = a_hi + (uint32_t)img_bytes;
+          for (int n = p.grp_first[g]; n < p.grp_first[g + 1]; ++n, ++it_b) {
+            const int sb = it_b % p.nb_stages;
+            mbar_wait(&full_b[sb], (it_b / p.nb_stages) & 1);
+            tc_fence_after();
+            const uint32_t b_hi = smem_u32(b_base + (size_t)sb * b_stage_bytes);
+            const uint32_t b_lo = b_hi + (uint32_t)(p.NT * 128);
+            const uint32_t shift = (uint32_t)p.tap_shift[n] * 128u;
 #pragma unroll
-          for (int kk = 0; kk < kTcKC / 16; ++kk) {
-            const uint32_t ko = (uint32_t)kk * 32u;
-            const uint64_t da_hi = smem_desc_sw128(a_hi + shift + ko, 16, 1024, use_bo);
-            const uint64_t da_lo = smem_desc_sw128(a_lo + shift + ko, 16, 1024, use_bo);
-            const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024, use_bo);
-            const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 16, 1024, use_bo);
-            umma_bf16(tmem_acc, da_lo, db_hi, idesc, acc);
-            acc = 1;
-            umma_bf16(tmem_acc, da_hi, db_lo, idesc, 1);
-            umma_bf16(tmem_acc, da_hi, db_hi, idesc, 1);
+            for (int kk = 0; kk < kTcKC / 16; ++kk) {
+              const uint32_t ko = (uint32_t)kk * 32u;
+              const uint64_t da_hi = smem_desc_sw128(a_hi + shift + ko, 16, 1024, false);
+              const uint64_t da_lo = smem_desc_sw128(a_lo + shift + ko, 16, 1024, false);
+              const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024, false);
+              const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 16, 1024, false);
+              umma_bf16(tmem_acc, da_lo, db_hi, idesc, acc);
+              acc = 1;
+              umma_bf16(tmem_acc, da_hi, db_lo, idesc, 1);
+              umma_bf16(tmem_acc, da_hi, db_hi, idesc, 1);
+            }
+            umma_commit(&empty_b[sb]);
           }
-          umma_commit(&empty_b[sb]);
+          umma_commit(&empty_a[sa]);
         }
-        umma_commit(&empty_a[sa]);
       }
       umma_commit(tmem_full);
     }
@@ -258,21 +275,61 @@ static int pick_nt(int n) {
   return 0;
 }
 
+std::vector<Phase> conv_phases(const KtConv1dDesc* d, int dir);  // conv_ffma.cu
+
+// Phase -> residue groups.  Returns false when the phase does not fit the kernel's limits.
+static bool fill_groups(TcParams& p, const Phase& ph, int nsub) {
+  p.M = ph.M; p.o_off = ph.o_off; p.o_step = ph.o_step; p.i_step = ph.i_step; p.up = ph.up; p.accumulate = ph.accumulate;
+  const int s = ph.i_step;
+  if (s < 1 || s > kTcMaxGroups) return false;
+  int q[kMaxTaps], rho[kMaxTaps];
+  for (int n = 0; n < ph.ntaps; ++n) {
+    if (ph.tap_ioff[n] < -(1 << 24)) {  // placeholder tap of an output residue no real tap reaches
+      q[n] = -(1 << 20); rho[n] = 0;
+      continue;
+    }
+    q[n] = fdiv(ph.tap_ioff[n], s);
+    rho[n] = ph.tap_ioff[n] - q[n] * s;
+  }
+  p.ngroups = 0;
+  p.ntaps = 0;
+  int max_span = 0;
+  for (int r = 0; r < s; ++r) {
+    int qlo = 1 << 30, qhi = -(1 << 30), cnt = 0;
+    for (int n = 0; n < ph.ntaps; ++n)
+      if (rho[n] == r) { qlo = std::min(qlo, q[n]); qhi = std::max(qhi, q[n]); ++cnt; }
+    if (!cnt) continue;
+    const int g = p.ngroups++;
+    p.grp_rho[g] = r; p.grp_qlo[g] = qlo; p.grp_first[g] = p.ntaps;
+    for (int n = 0; n < ph.ntaps; ++n)
+      if (rho[n] == r) {
+        p.tap_j[p.ntaps] = ph.tap_j[n];
+        p.tap_shift[p.ntaps] = (q[n] - qlo) * nsub;
+        ++p.ntaps;
+      }
+    max_span = std::max(max_span, (qhi - qlo) * nsub);
+  }
+  p.grp_first[p.ngroups] = p.ntaps;
+  if (max_span > (1 << 20)) {  // a phase that no tap reaches (dummy tap far outside): keep one empty image
+    max_span = 0;
+    for (int n = 0; n < p.ntaps; ++n) p.tap_shift[n] = 0;
+  }
+  p.rows = (kTcM + max_span + 7) & ~7;
+  return p.rows <= kTcMaxRows;
+}
+
 // Is (direction dir: 0 fwd, 1 bwd_data) of this layer runnable on the tcgen05 kernel?  -> N tile or 0
 int tc_plan(const KtConv1dDesc* d, int dir) {
-  if (d->groups != 1 || d->upsample != 1) return 0;
+  if (d->groups != 1) return 0;
+  if (dir == 1 && d->upsample > 1) return 0;          // `upsample` single-tap residue phases: staging-bound, stays FFMA
   const int cin = dir == 0 ? d->c_in : d->c_out;     // contraction channels
   const int cout = dir == 0 ? d->c_out : d->c_in;    // produced channels
   if (cin % kTcKC != 0) return 0;
   const int nt = pick_nt(cout);
   if (nt == 0) return 0;
-  // gather phases must have unit input step: conv fwd / conv dgrad with stride 1, transposed fwd (any stride)
-  const bool scatter = (dir == 0) == (d->transposed != 0);
-  if (!scatter && d->stride != 1) return 0;
-  if (scatter && d->nsub != 1 && d->stride != 1) return 0;
-  if (d->nsub != 1 && d->stride != 1) return 0;
-  const long long halo = (long long)(d->kernel - 1) * d->dilation * d->nsub;
-  if (kTcM + halo > kTcMaxRows) return 0;
+  TcParams p{};
+  for (const Phase& ph : conv_phases(d, dir))
+    if (!fill_groups(p, ph, d->nsub)) return 0;
   return nt;
 }
 
@@ -286,21 +343,16 @@ int tc_pack_weights(const float* w, int taps, int K, int N, int NT, void* out, c
   return KT_OK;
 }
 
-std::vector<Phase> conv_phases(const KtConv1dDesc* d, int dir);  // conv_ffma.cu
-
-static int run_tc(TcParams p, cudaStream_t st) {
-  const Phase& ph = p.ph;
+static int run_tc(TcParams p, const Phase& ph, cudaStream_t st) {
   if (ph.M <= 0) return KT_OK;
-  KT_REQUIRE(ph.i_step == 1 && ph.up == 1, "conv_tc: phase must have unit input step");
-  p.rows = (kTcM + (ph.max_ioff - ph.min_ioff) + 7) & ~7;
-  KT_REQUIRE(p.rows <= kTcMaxRows, "conv_tc: halo too large (%d rows)", p.rows);
+  KT_REQUIRE(fill_groups(p, ph, p.nsub), "conv_tc: phase exceeds kernel limits (input step %d)", ph.i_step);
   p.kchunks = p.c_in / kTcKC;
   p.ntiles = p.c_out / p.NT;
   p.tmem_cols = 32;
   while (p.tmem_cols < p.NT) p.tmem_cols <<= 1;
   const int a_bytes = 2 * 2 * p.rows * 128;
   const int b_stage = 2 * p.NT * 128;
-  const int budget = 227 * 1024 - 1024 /*align slack*/ - a_bytes - 256 /*barriers*/;
+  const int budget = kMaxDynSmem - 1024 /*align slack*/ - a_bytes - 256 /*barriers*/;
   p.nb_stages = std::min(6, budget / b_stage);
   KT_REQUIRE(p.nb_stages >= 2, "conv_tc: shared memory budget exceeded (rows=%d NT=%d)", p.rows, p.NT);
   const size_t smem = 1024 + a_bytes + (size_t)p.nb_stages * b_stage + 256;
@@ -309,7 +361,7 @@ static int run_tc(TcParams p, cudaStream_t st) {
     KT_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     cfg.store(true, std::memory_order_release);
   }
-  dim3 grid(ceil_div(ph.M, kTcM), p.ntiles, p.batch);
+  dim3 grid(ceil_div(p.M * p.nsub, kTcM), p.ntiles, p.batch);
   conv_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
   KT_CHECK_CUDA(cudaGetLastError());
   return KT_OK;
@@ -323,64 +375,39 @@ static Side make_side_tc(const float* p, const float* aux, int act, float slope,
   return s;
 }
 
-static int tc_flags() {
-  static int flags = -1;
-  if (flags < 0) {
-    // Measured on B200 (round 1, profiles/r01_notes.md): the SWIZZLE_128B XOR is applied to ABSOLUTE
-    // shared-memory address bits, so a row-shifted descriptor needs matrix-base-offset = 0; setting it
-    // to (addr >> 7) & 7 double-applies the phase and gives wrong results.  Env override kept for the record.
-    const char* e = getenv("KT_TC_BASE_OFFSET");
-    flags = (e && e[0] == '1') ? 1 : 0;
-  }
-  return flags;
-}
-
-// nsub > 1 with stride 1 folds into a plain sequence of t*nsub rows with dilation*nsub
-static KtConv1dDesc fold_nsub(const KtConv1dDesc* d) {
-  KtConv1dDesc f = *d;
-  if (d->nsub > 1) {
-    f.t_in = d->t_in * d->nsub; f.t_out = d->t_out * d->nsub;
-    f.dilation = d->dilation * d->nsub; f.pad_left = d->pad_left * d->nsub; f.nsub = 1;
-  }
-  return f;
-}
-
-int conv1d_fwd_tc(const KtConv1dDesc* d0, const float* x, const void* wimg, const float* bias, const float* resid,
+int conv1d_fwd_tc(const KtConv1dDesc* d, const float* x, const void* wimg, const float* bias, const float* resid,
                   float* y, cudaStream_t st) {
-  const int nt = tc_plan(d0, 0);
+  const int nt = tc_plan(d, 0);
   KT_REQUIRE(nt > 0, "conv1d_fwd_tc: layer not supported by the tcgen05 path");
-  const KtConv1dDesc f = fold_nsub(d0);
   TcParams p{};
-  p.in = make_side_tc(x, nullptr, f.act_in, f.act_in_slope, false);
+  p.in = make_side_tc(x, nullptr, d->act_in, d->act_in_slope, false);
   p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
   p.bias = bias; p.resid = resid; p.mask = Side{nullptr, nullptr, 0, 0.f}; p.out = y;
-  p.batch = f.batch; p.t_in = f.t_in; p.t_out = f.t_out; p.c_in = f.c_in; p.c_out = f.c_out;
-  p.out_act = f.act_out; p.out_slope = f.act_out_slope; p.NT = nt; p.flags = tc_flags();
-  for (const Phase& ph : conv_phases(&f, 0)) {
-    p.ph = ph;
-    int rc = run_tc(p, st);
+  p.batch = d->batch; p.nsub = d->nsub; p.t_in = d->t_in; p.t_out = d->t_out; p.c_in = d->c_in; p.c_out = d->c_out;
+  p.out_act = d->act_out; p.out_slope = d->act_out_slope; p.NT = nt;
+  for (const Phase& ph : conv_phases(d, 0)) {
+    int rc = run_tc(p, ph, st);
     if (rc) return rc;
   }
   return KT_OK;
 }
 
-int conv1d_bwd_data_tc(const KtConv1dDesc* d0, const float* dy, const float* y, const void* wimg, const float* x,
+int conv1d_bwd_data_tc(const KtConv1dDesc* d, const float* dy, const float* y, const void* wimg, const float* x,
                        float* dx, cudaStream_t st) {
-  const int nt = tc_plan(d0, 1);
+  const int nt = tc_plan(d, 1);
   KT_REQUIRE(nt > 0, "conv1d_bwd_data_tc: layer not supported by the tcgen05 path");
-  KT_REQUIRE(d0->act_out == KT_ACT_NONE || y != nullptr, "bwd_data: y required when act_out != NONE");
-  KT_REQUIRE(d0->act_in == KT_ACT_NONE || x != nullptr, "bwd_data: x required when act_in != NONE");
-  const KtConv1dDesc f = fold_nsub(d0);
+  KT_REQUIRE(d->act_out == KT_ACT_NONE || y != nullptr, "bwd_data: y required when act_out != NONE");
+  KT_REQUIRE(d->act_in == KT_ACT_NONE || x != nullptr, "bwd_data: x required when act_in != NONE");
   TcParams p{};
-  p.in = make_side_tc(dy, y, f.act_out, f.act_out_slope, true);
+  p.in = make_side_tc(dy, y, d->act_out, d->act_out_slope, true);
   p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
   p.bias = nullptr; p.resid = nullptr; p.out = dx;
-  p.mask = f.act_in == KT_ACT_LRELU ? Side{x, nullptr, SIDE_DLRELU, f.act_in_slope} : Side{nullptr, nullptr, 0, 0.f};
-  p.batch = f.batch; p.t_in = f.t_out; p.t_out = f.t_in; p.c_in = f.c_out; p.c_out = f.c_in;
-  p.out_act = KT_ACT_NONE; p.out_slope = 0.f; p.NT = nt; p.flags = tc_flags();
-  for (const Phase& ph : conv_phases(&f, 1)) {
-    p.ph = ph;
-    int rc = run_tc(p, st);
+  p.mask = d->act_in == KT_ACT_LRELU ? Side{x, nullptr, SIDE_DLRELU, d->act_in_slope} : Side{nullptr, nullptr, 0, 0.f};
+  // roles swap: the gathered tensor is dy (c_out channels, t_out rows), the product is dx
+  p.batch = d->batch; p.nsub = d->nsub; p.t_in = d->t_out; p.t_out = d->t_in; p.c_in = d->c_out; p.c_out = d->c_in;
+  p.out_act = KT_ACT_NONE; p.out_slope = 0.f; p.NT = nt;
+  for (const Phase& ph : conv_phases(d, 1)) {
+    int rc = run_tc(p, ph, st);
     if (rc) return rc;
   }
   return KT_OK;

@@ -160,10 +160,33 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
 // Loads are issued in batches of NB rows per thread BEFORE any conversion so that each thread keeps
 // 2*NB (4*NB with an aux tensor) 16-byte loads in flight: with one 192-thread CTA per SM the
 // staging loop is otherwise pure DRAM/L2 latency.
+//
+// RowMap: image row r -> source row of the channels-last tensor.  The rows of a tile are the
+// FLATTENED (time m', sub-sequence w) index fv = m' * nsub + w of one batch item (nsub = period of the
+// period discriminator, else 1); the source time is t = m' * step + rho (a strided conv reads one
+// residue class rho of the input per image), optionally nearest-upsampled (t / up):
+//     fv = fv0 + r;  m' = floor(fv / nsub);  w = fv mod nsub;  tv = m' * step + rho  (valid iff 0 <= tv < t_lim)
+//     source row = base_row + (tv / up) * nsub + w
+// With this map a conv tap (q, rho) is the row shift q * nsub of residue image rho for ANY stride and
+// period, so every M = 128 tile is a dense run of flattened outputs.
+struct RowMap {
+  long long base_row;
+  int fv0, nsub, step, rho, up, t_lim;
+  __device__ __forceinline__ bool map(int r, long long& row) const {
+    const int fv = fv0 + r;
+    const int mp = nsub == 1 ? fv : fdiv(fv, nsub);
+    const int w = fv - mp * nsub;
+    const int tv = mp * step + rho;
+    if (tv < 0 || tv >= t_lim) return false;
+    row = base_row + (long long)(up == 1 ? tv : tv / up) * nsub + w;
+    return true;
+  }
+};
+
 template <int NB>
 __device__ __forceinline__ void stage_rows(uint8_t* img_hi, uint8_t* img_lo, const Side& s, const float* base,
-                                           const float* aux_base, int c_total, int ch0, int t0, int t_valid_lo,
-                                           int t_valid_hi, int rows, int tid) {
+                                           const float* aux_base, int c_total, int ch0, const RowMap& rm, int rows,
+                                           int tid) {
   const int q = tid & 7;
   const bool has_aux = s.mode >= SIDE_DLRELU;
   for (int r0 = tid >> 3; r0 < rows; r0 += 16 * NB) {
@@ -171,9 +194,9 @@ __device__ __forceinline__ void stage_rows(uint8_t* img_hi, uint8_t* img_lo, con
 #pragma unroll
     for (int i = 0; i < NB; ++i) {
       const int r = r0 + 16 * i;
-      const int t = t0 + r;
-      const bool ok = r < rows && t >= t_valid_lo && t < t_valid_hi;
-      const long long off = ok ? (long long)t * c_total + ch0 + q * 8 : 0;
+      long long srow = 0;
+      const bool ok = r < rows && rm.map(r, srow);
+      const long long off = ok ? srow * c_total + ch0 + q * 8 : 0;
       v[i][0] = ok ? __ldg(reinterpret_cast<const float4*>(base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
       v[i][1] = ok ? __ldg(reinterpret_cast<const float4*>(base + off + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (has_aux) {

@@ -1,17 +1,19 @@
 // tcgen05 weight-gradient kernel (bf16x3 split precision, fp32 accumulation in TMEM).
 //
-//   dW[tap j][ca][cb] = sum_{batch, m}  fa(A[b][m + ioff_j][ca]) * fb(Bm[b][m][cb])
-//   conv layer:  A = act_in(x) (rows = input time, channels ca = C_in),  Bm = dy * act_out'(y) (C_out)
+//   G[tap j][ca][cb] = sum_{batch, w, m}  fa(A[b][(m*step + ioff_j)/up, w][ca]) * fb(Bm[b][m, w][cb])
+//   conv layer      : A = act_in(x)  (ca = C_in),  Bm = dy * act_out'(y) (cb = C_out), step = stride
+//   transposed conv : A = dy * act'  (ca = C_out), Bm = act_in(x)        (cb = C_in),  step = stride
 //
-// The contraction runs over TIME, so both MMA operands are "MN-major" views of the same kind of
-// shared-memory image the forward kernel uses ([time rows][64 channels] bf16, SWIZZLE_128B):
-// K = 16 consecutive rows per tcgen05.mma, M / N = channels (64-element groups, LBO apart).
-// A conv tap is again a pure descriptor row shift of the staged A image.  Two ways to fill M = 128:
-//   mode 0 (C_in >= 128): two 64-channel images of one tap (LBO = image stride)
-//   mode 1 (C_in == 64) : ONE image, two taps: LBO = (ioff_{j+1} - ioff_j) * 128 bytes
-// Each CTA owns (ca tile, cb tile, a group of U "units" = U*NT TMEM columns <= 512) for a slice of the
-// (batch, time) range (split-K); partial tiles go to a workspace with plain 16-byte stores and a
-// second kernel reduces over the splits (cheaper than ~10^7 fp32 atomics per launch).
+// The contraction runs over the flattened (time, sub-sequence) index, so both MMA operands are
+// "MN-major" views of the same kind of shared-memory image the forward kernel uses ([flattened rows]
+// [64 channels] bf16, SWIZZLE_128B): K = 16 consecutive rows per tcgen05.mma, M / N = channels
+// (64-element groups, LBO apart).  A conv tap (q, rho) is again a pure descriptor row shift (q * nsub)
+// of the staged residue image rho.  Two ways to fill M = 128:
+//   mode 0 (ca % 128 == 0): two 64-channel images of one tap (LBO = image stride)
+//   mode 1 (ca == 64)     : ONE image, two taps of the same residue: LBO = (q_{n+1} - q_n) * nsub * 128 B
+// Each CTA owns (ca tile, cb tile, a group of <= U "units" of one residue class = U*NT TMEM columns
+// <= 512) for a slice of the (batch, flattened time) range (split-K); partial tiles go to a workspace
+// with plain 16-byte stores and a second kernel reduces over the splits (cheaper than ~10^7 atomics).
 #include <algorithm>
 #include <atomic>
 #include <vector>
@@ -23,24 +25,29 @@ namespace kt {
 
 using namespace tc;
 
-constexpr int kWgTK = 64;        // time rows per staged chunk
+constexpr int kWgTK = 64;        // flattened rows per staged chunk
 constexpr int kWgThreads = 192;
 constexpr int kWgMaxUnits = 8;
+constexpr int kWgMaxGroups = 24;
 
 struct WgTcParams {
   Side a, b;
   float* ws;
-  int batch, t_a, t_b, ca, cb, taps_total;
-  int M;                       // base rows per batch item
+  int batch, nsub, t_a, t_b, ca, cb, taps_total;
+  int M;                       // base rows m per sub-sequence
+  int step, up;
   int mode, NT, n_cb_tiles, n_ca_tiles;
-  int units_total, units_per_cta;
   int nsplit, chunks_per_batch;
   int a_groups, b_groups;      // 64-channel images per stage on each side
-  int rows_a;                  // A image rows (TK + halo, multiple of 8)
+  int rows_a;                  // A image rows (max over unit groups), multiple of 8
   int tmem_cols;
-  int ntaps;
+  int ngroups;                 // unit groups (grid.y)
+  int grp_rho[kWgMaxGroups], grp_qlo[kWgMaxGroups];
+  int grp_first_unit[kWgMaxGroups + 1];
+  int unit_tap0[kMaxTaps];     // first tap (index into tap_j / tap_q) of each unit
+  int unit_ntaps[kMaxTaps];    // 1 or 2
   int tap_j[kMaxTaps];
-  int tap_ioff[kMaxTaps];      // ascending
+  int tap_q[kMaxTaps];
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
@@ -59,16 +66,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ca_tile = blockIdx.x / p.n_cb_tiles;
   const int cb_tile = blockIdx.x % p.n_cb_tiles;
-  const int u0 = blockIdx.y * p.units_per_cta;
-  const int nu = min(p.units_per_cta, p.units_total - u0);
+  const int grp = blockIdx.y;
+  const int u0 = p.grp_first_unit[grp];
+  const int nu = p.grp_first_unit[grp + 1] - u0;
+  const int qlo = p.grp_qlo[grp];
   const int split = blockIdx.z;
-
-  // taps covered by this CTA and their row-offset range
-  const int taps_per_unit = p.mode == 1 ? 2 : 1;
-  const int n_first = u0 * taps_per_unit;
-  const int n_last = min((u0 + nu) * taps_per_unit, p.ntaps) - 1;
-  const int gmin = p.tap_ioff[n_first];
-  const int gmax = p.tap_ioff[n_last];
 
   const long long units = (long long)p.batch * p.chunks_per_batch;
   const long long c_begin = units * split / p.nsplit;
@@ -93,23 +95,23 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       const int s = it & 1;
       mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
       const int bb = (int)(c / p.chunks_per_batch);
-      const int m0 = (int)(c % p.chunks_per_batch) * kWgTK;
+      const int f0 = (int)(c % p.chunks_per_batch) * kWgTK;
       uint8_t* st = stage0 + (size_t)s * stage_bytes;
-      const float* a_base = p.a.p + (long long)bb * p.t_a * p.ca;
-      const float* a_aux = p.a.aux ? p.a.aux + (long long)bb * p.t_a * p.ca : nullptr;
-      const float* b_base = p.b.p + (long long)bb * p.t_b * p.cb;
-      const float* b_aux = p.b.aux ? p.b.aux + (long long)bb * p.t_b * p.cb : nullptr;
-      // A images: rows t = m0 + gmin + r.  Rows whose base row m = t - ioff would be >= M only meet
-      // zero B rows, so plain [0, t_a) validity is enough.
+      RowMap ra;  // gathered side: residue image of this unit group
+      ra.base_row = (long long)bb * p.t_a * p.nsub;
+      ra.fv0 = f0 + qlo * p.nsub;
+      ra.nsub = p.nsub; ra.step = p.step; ra.rho = p.grp_rho[grp]; ra.up = p.up; ra.t_lim = p.t_a * p.up;
       for (int g = 0; g < p.a_groups; ++g) {
         uint8_t* hi = st + (size_t)g * 2 * img_a;
-        stage_rows<5>(hi, hi + img_a, p.a, a_base, a_aux, p.ca, ca_tile * (p.mode == 0 ? 128 : 64) + g * 64, m0 + gmin, 0,
-                   p.t_a, p.rows_a, tid);
+        stage_rows<5>(hi, hi + img_a, p.a, p.a.p, p.a.aux, p.ca, ca_tile * (p.mode == 0 ? 128 : 64) + g * 64, ra, p.rows_a, tid);
       }
+      RowMap rb;  // base side: rows m (flattened with w), zero beyond M
+      rb.base_row = (long long)bb * p.t_b * p.nsub;
+      rb.fv0 = f0; rb.nsub = p.nsub; rb.step = 1; rb.rho = 0; rb.up = 1; rb.t_lim = min(p.M, p.t_b);
       uint8_t* bst = st + (size_t)p.a_groups * 2 * img_a;
       for (int g = 0; g < p.b_groups; ++g) {
         uint8_t* hi = bst + (size_t)g * 2 * img_b;
-        stage_rows<4>(hi, hi + img_b, p.b, b_base, b_aux, p.cb, cb_tile * p.NT + g * 64, m0, 0, min(p.M, p.t_b), kWgTK, tid);
+        stage_rows<4>(hi, hi + img_b, p.b, p.b.p, p.b.aux, p.cb, cb_tile * p.NT + g * 64, rb, kWgTK, tid);
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);
@@ -122,9 +124,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     const uint32_t t_lane = tmem_acc + ((uint32_t)(warp * 32) << 16);
     for (int u = 0; u < nu; ++u) {
       int tap_n, ca_idx;
-      if (p.mode == 0) { tap_n = u0 + u; ca_idx = ca_tile * 128 + row; }
-      else { tap_n = (u0 + u) * 2 + (row >> 6); ca_idx = row & 63; }
-      const bool valid = tap_n < p.ntaps;
+      bool valid;
+      if (p.mode == 0) { tap_n = p.unit_tap0[u0 + u]; ca_idx = ca_tile * 128 + row; valid = true; }
+      else { tap_n = p.unit_tap0[u0 + u] + (row >> 6); ca_idx = row & 63; valid = (row >> 6) < p.unit_ntaps[u0 + u]; }
       const long long obase = valid ? (((long long)split * p.taps_total + p.tap_j[tap_n]) * p.ca + ca_idx) * p.cb + (long long)cb_tile * p.NT : 0;
       for (int n0 = 0; n0 < p.NT; n0 += 32) {
         uint32_t rr[32];
@@ -153,18 +155,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         const uint32_t b_hi = st + (uint32_t)(p.a_groups * 2 * img_a);
         const uint32_t b_lo = b_hi + (uint32_t)img_b;
         for (int u = 0; u < nu; ++u) {
-          int n_a;
+          const int n_a = p.unit_tap0[u0 + u];
           uint32_t lbo_a;
           if (p.mode == 0) {
-            n_a = u0 + u;
             lbo_a = 2u * (uint32_t)img_a;
           } else {
-            n_a = (u0 + u) * 2;
-            const int n_b2 = min(n_a + 1, p.ntaps - 1);
-            lbo_a = (uint32_t)(p.tap_ioff[n_b2] - p.tap_ioff[n_a]) * 128u;
-            if (lbo_a == 0) lbo_a = 128u;  // odd tap count: rows 64..127 of the last unit are discarded
+            // second half of M = the next tap of the same residue (rows 64..127 are discarded when the unit has one tap)
+            lbo_a = p.unit_ntaps[u0 + u] == 2 ? (uint32_t)((p.tap_q[n_a + 1] - p.tap_q[n_a]) * p.nsub) * 128u : 128u;
           }
-          const uint32_t shift = (uint32_t)(p.tap_ioff[n_a] - gmin) * 128u;
+          const uint32_t shift = (uint32_t)((p.tap_q[n_a] - qlo) * p.nsub) * 128u;
           const uint32_t a_hi = st + shift;
           const uint32_t a_lo = a_hi + (uint32_t)img_a;
           const uint32_t d = tmem_acc + (uint32_t)(u * p.NT);
@@ -217,53 +216,77 @@ struct WgPlan {
   long long ws_floats;
 };
 
-std::vector<Phase> conv_phases(const KtConv1dDesc* d, int dir);
-
-static WgPlan make_plan(const KtConv1dDesc* d0) {
+static WgPlan make_plan(const KtConv1dDesc* d) {
   WgPlan pl{};
   pl.ok = false;
-  if (d0->transposed || d0->groups != 1 || d0->upsample != 1 || d0->stride != 1) return pl;
-  KtConv1dDesc d = *d0;
-  if (d.nsub > 1) {  // stride-1 period conv folds to dilation * nsub (see conv_tc.cu)
-    d.t_in *= d.nsub; d.t_out *= d.nsub; d.dilation *= d.nsub; d.pad_left *= d.nsub; d.nsub = 1;
-  }
-  const int ca = d.c_in, cb = d.c_out;
+  if (d->groups != 1) return pl;
+  WgTcParams& p = pl.p;
+  // gathered (A) side / base (B) side, see conv_ffma.cu: conv1d_bwd_weight_ffma
+  const bool tr = d->transposed != 0;
+  const int ca = tr ? d->c_out : d->c_in, cb = tr ? d->c_in : d->c_out;
   if (ca % 64 != 0 || cb % 64 != 0) return pl;
   if (ca != 64 && ca % 128 != 0) return pl;
-  WgTcParams& p = pl.p;
-  p.batch = d.batch; p.t_a = d.t_in; p.t_b = d.t_out; p.ca = ca; p.cb = cb; p.taps_total = d.kernel;
-  p.M = d.t_out;
-  p.ntaps = d.kernel;
-  for (int j = 0; j < d.kernel; ++j) { p.tap_j[j] = j; p.tap_ioff[j] = j * d.dilation - d.pad_left; }
+  p.batch = d->batch; p.nsub = d->nsub; p.ca = ca; p.cb = cb; p.taps_total = d->kernel;
+  p.t_a = tr ? d->t_out : d->t_in;
+  p.t_b = tr ? d->t_in : d->t_out;
+  p.M = p.t_b;
+  p.step = d->stride;
+  p.up = tr ? 1 : d->upsample;
+  if (p.step > 8) return pl;
   p.mode = ca == 64 ? 1 : 0;
   p.NT = cb % 256 == 0 ? 256 : (cb % 128 == 0 ? 128 : 64);
-  if (cb < p.NT) p.NT = cb;
   p.n_cb_tiles = cb / p.NT;
   p.n_ca_tiles = p.mode == 0 ? ca / 128 : 1;
-  p.units_total = p.mode == 0 ? p.ntaps : (p.ntaps + 1) / 2;
   p.a_groups = p.mode == 0 ? 2 : 1;
   p.b_groups = p.NT / 64;
-  // shared memory: 2 stages of (A images with halo + B images); shrink units per CTA until it fits
-  int U = std::min({kWgMaxUnits, 512 / p.NT, p.units_total});
-  for (; U >= 1; --U) {
-    const int taps_per_unit = p.mode == 1 ? 2 : 1;
-    const int span_taps = std::min(U * taps_per_unit, p.ntaps);
-    const int halo = (span_taps - 1) * d.dilation;
-    const int rows_a = (kWgTK + halo + 7) & ~7;
-    const size_t stage = 2 * ((size_t)p.a_groups * rows_a * 128 + (size_t)p.b_groups * kWgTK * 128);
-    const size_t smem = 1024 + 2 * stage + 128;
-    if (smem <= (size_t)kMaxDynSmem) {
-      p.units_per_cta = U; p.rows_a = rows_a; pl.smem = smem;
-      break;
+  const int U = std::min(kWgMaxUnits, 512 / p.NT);
+  const int taps_per_unit = p.mode == 1 ? 2 : 1;
+  // taps sorted by (residue, q)
+  int ntap = 0, nunit = 0;
+  p.ngroups = 0;
+  int max_span = 0;
+  for (int r = 0; r < p.step; ++r) {
+    std::vector<std::pair<int, int>> tq;  // (q, j)
+    for (int j = 0; j < d->kernel; ++j) {
+      const int ioff = j * d->dilation - d->pad_left;
+      const int q = fdiv(ioff, p.step);
+      if (ioff - q * p.step == r) tq.push_back({q, j});
+    }
+    std::sort(tq.begin(), tq.end());
+    size_t i = 0;
+    while (i < tq.size()) {
+      // one unit group: up to U units of this residue
+      if (p.ngroups >= kWgMaxGroups) return pl;
+      const int g = p.ngroups++;
+      p.grp_rho[g] = r;
+      p.grp_qlo[g] = tq[i].first;
+      p.grp_first_unit[g] = nunit;
+      int qhi = tq[i].first;
+      for (int u = 0; u < U && i < tq.size(); ++u) {
+        p.unit_tap0[nunit] = ntap;
+        const int nt_u = (int)std::min<size_t>(taps_per_unit, tq.size() - i);
+        p.unit_ntaps[nunit] = nt_u;
+        for (int e = 0; e < nt_u; ++e, ++i, ++ntap) {
+          p.tap_j[ntap] = tq[i].second;
+          p.tap_q[ntap] = tq[i].first;
+          qhi = tq[i].first;
+        }
+        ++nunit;
+      }
+      max_span = std::max(max_span, (qhi - p.grp_qlo[g]) * p.nsub);
     }
   }
-  if (U < 1) return pl;
+  p.grp_first_unit[p.ngroups] = nunit;
+  p.rows_a = (kWgTK + max_span + 7) & ~7;
+  const size_t stage = 2 * ((size_t)p.a_groups * p.rows_a * 128 + (size_t)p.b_groups * kWgTK * 128);
+  pl.smem = 1024 + 2 * stage + 128;
+  if (pl.smem > (size_t)kMaxDynSmem) return pl;   // (a smaller U would shrink the halo; not needed for the shipped shapes)
   p.tmem_cols = 32;
-  while (p.tmem_cols < p.units_per_cta * p.NT) p.tmem_cols <<= 1;
+  while (p.tmem_cols < U * p.NT) p.tmem_cols <<= 1;
   if (p.tmem_cols > 512) return pl;
-  p.chunks_per_batch = ceil_div(p.M, kWgTK);
+  p.chunks_per_batch = ceil_div(p.M * p.nsub, kWgTK);
   const long long units = (long long)p.batch * p.chunks_per_batch;
-  const long long base = (long long)p.n_ca_tiles * p.n_cb_tiles * ceil_div(p.units_total, p.units_per_cta);
+  const long long base = (long long)p.n_ca_tiles * p.n_cb_tiles * p.ngroups;
   long long nsplit = std::max<long long>(1, (148 + base - 1) / base);
   nsplit = std::min(nsplit, units);
   p.nsplit = (int)nsplit;
@@ -287,18 +310,20 @@ int conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy,
   KT_REQUIRE(ws && ws_floats >= pl.ws_floats, "conv1d_bwd_weight_tc: workspace too small (%lld < %lld floats)", ws_floats, pl.ws_floats);
   KT_REQUIRE(d->act_out == KT_ACT_NONE || y != nullptr, "bwd_weight: y required when act_out != NONE");
   WgTcParams& p = pl.p;
-  p.a = Side{x, nullptr, d->act_in == KT_ACT_LRELU ? SIDE_LRELU : SIDE_PLAIN, d->act_in_slope};
-  p.b = Side{dy, y, SIDE_PLAIN, d->act_out_slope};
-  if (d->act_out == KT_ACT_LRELU) p.b.mode = SIDE_DLRELU;
-  else if (d->act_out == KT_ACT_TANH) p.b.mode = SIDE_DTANH;
-  else p.b.aux = nullptr;
+  const Side sx{x, nullptr, d->act_in == KT_ACT_LRELU ? SIDE_LRELU : SIDE_PLAIN, d->act_in_slope};
+  Side sdy{dy, y, SIDE_PLAIN, d->act_out_slope};
+  if (d->act_out == KT_ACT_LRELU) sdy.mode = SIDE_DLRELU;
+  else if (d->act_out == KT_ACT_TANH) sdy.mode = SIDE_DTANH;
+  else sdy.aux = nullptr;
+  if (d->transposed) { p.a = sdy; p.b = sx; }
+  else { p.a = sx; p.b = sdy; }
   p.ws = ws;
   static std::atomic<bool> cfg{false};
   if (!cfg.load(std::memory_order_acquire)) {
     KT_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     cfg.store(true, std::memory_order_release);
   }
-  dim3 grid(p.n_ca_tiles * p.n_cb_tiles, ceil_div(p.units_total, p.units_per_cta), p.nsplit);
+  dim3 grid(p.n_ca_tiles * p.n_cb_tiles, p.ngroups, p.nsplit);
   wgrad_tc_kernel<<<grid, kWgThreads, pl.smem, st>>>(p);
   KT_CHECK_CUDA(cudaGetLastError());
   const long long n = (long long)p.taps_total * p.ca * p.cb;
@@ -307,7 +332,7 @@ int conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy,
   KT_CHECK_CUDA(cudaGetLastError());
   if (dbias) {
     const long long rows = (long long)d->batch * d->nsub * d->t_out;
-    int rc = colsum_bias(p.b, rows, d->c_out, dbias, st);
+    int rc = colsum_bias(sdy, rows, d->c_out, dbias, st);
     if (rc) return rc;
   }
   return KT_OK;

@@ -52,6 +52,11 @@ CASES = {
     "tc_256_k3": (dict(c_in=256, c_out=256, kernel=3, pad_left=2, act_in=0.1), 2, 256, 0, True, True),
     "tc_64_to_192": (dict(c_in=64, c_out=192, kernel=7, dilation=1, pad_left=3, pad_right=3), 1, 200, 0, False, True),
     "tc_512_to_1024_k5": (dict(c_in=512, c_out=1024, kernel=5, pad_left=2, pad_right=2, act_out=0.1), 1, 140, 0, False, True),
+    "tc_period_s3": (dict(c_in=128, c_out=256, kernel=5, stride=3, pad_left=2, pad_right=2, act_out=0.1), 2, 100, 3, False, True),
+    "tc_period_s3_p11": (dict(c_in=64, c_out=128, kernel=5, stride=3, pad_left=2, pad_right=2, act_out=0.1), 2, 83, 11, False, True),
+    "tc_strided_s4_k9": (dict(c_in=64, c_out=64, kernel=9, stride=4, pad_left=4, pad_right=4, act_out=0.1), 2, 500, 0, False, True),
+    "tc_upsample_conv": (dict(c_in=128, c_out=64, kernel=7, pad_left=6, upsample=2, act_in=0.1), 2, 300, 0, False, True),
+    "tc_deconv_128_64_k4s2": (dict(c_in=128, c_out=64, kernel=4, stride=2, transposed=True, crop=2, act_in=0.1), 2, 300, 0, True, True),
     "tc_deconv_256_128": (dict(c_in=256, c_out=128, kernel=16, stride=8, transposed=True, crop=8, act_in=0.1), 2, 32, 0, True, True),
 }
 
@@ -106,11 +111,15 @@ def _run_case(name, force_ffma):
         ops.set_force_ffma(False)
     tol = 1e-4 if used_tc else 2e-5
     assert rel_l2(_from_rows(y).cpu(), yo) < tol, ("y", rel_l2(_from_rows(y).cpu(), yo))
-    assert rel_l2(_from_rows(xg.grad).cpu(), xo.grad) < tol, ("dx", rel_l2(_from_rows(xg.grad).cpu(), xo.grad))
-    assert rel_l2(vg.grad.cpu(), vo.grad) < 5e-5, ("dv", rel_l2(vg.grad.cpu(), vo.grad))
-    assert rel_l2(bg.grad.cpu(), bo.grad) < 5e-5, "dbias"
+    # a fused output LeakyReLU makes the backward mask depend on sign(y): the handful of |y| ~ 1e-5 elements
+    # whose sign differs between the bf16x3 and the fp32 forward change dpre discontinuously
+    tol_dx = 5e-4 if (used_tc and act_out is not None) else tol
+    assert rel_l2(_from_rows(xg.grad).cpu(), xo.grad) < tol_dx, ("dx", rel_l2(_from_rows(xg.grad).cpu(), xo.grad))
+    tol_w = 3e-4 if used_tc else 5e-5
+    assert rel_l2(vg.grad.cpu(), vo.grad) < tol_w, ("dv", rel_l2(vg.grad.cpu(), vo.grad))
+    assert rel_l2(bg.grad.cpu(), bo.grad) < tol_w, "dbias"
     if wn:
-        assert rel_l2(g2.grad.cpu(), go.grad) < 5e-5, "dg"
+        assert rel_l2(g2.grad.cpu(), go.grad) < tol_w, "dg"
     if use_resid:
         assert rel_l2(_from_rows(rg.grad).cpu(), ro.grad) < 1e-6, "dresid"
     return used_tc
