@@ -73,7 +73,7 @@ struct TcParams {
   int batch, nsub, t_in, t_out, c_in, c_out;
   int out_act;
   float out_slope;
-  int NT, ntiles, kchunks, rows, nb_stages, tmem_cols;
+  int NT, ntiles, kchunks, rows, na_stages, nb_stages, tmem_cols;
   // phase: out[(o_off + o_step*m), w] = sum_n W[tap_j[n]] in[(m + q_n)*i_step + rho_n, w]
   int M, o_off, o_step, i_step, up, accumulate;
   int ngroups;                        // residue classes actually used
@@ -85,8 +85,11 @@ struct TcParams {
   int tap_shift[kMaxTaps];            // image row shift (q_n - q_lo) * nsub
 };
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;  // warps 0-3 stage activations, 4 streams weights, 5 issues MMAs, 6-9 epilogue
 
+// Persistent: gridDim.x = min(#tiles, #SMs); each CTA walks tiles blockIdx.x, +gridDim.x, ...  The three
+// pipelines (activation images, weight tiles, TMEM accumulators: 2 buffers) run continuously ACROSS tiles,
+// so staging of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap.
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up (all image / tile bases 1024-byte aligned)
@@ -95,25 +98,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   const int a_stage_bytes = 2 * img_bytes;            // hi + lo
   const int b_stage_bytes = 2 * p.NT * 128;           // hi + lo weight tile
   uint8_t* a_base = smem;
-  uint8_t* b_base = a_base + 2 * a_stage_bytes;
+  uint8_t* b_base = a_base + (size_t)p.na_stages * a_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)p.nb_stages * b_stage_bytes);
-  uint64_t* full_a = bars;            // [2]
-  uint64_t* empty_a = bars + 2;       // [2]
-  uint64_t* full_b = bars + 4;        // [nb]
-  uint64_t* empty_b = full_b + p.nb_stages;
-  uint64_t* tmem_full = empty_b + p.nb_stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* full_a = bars;                         // [na]
+  uint64_t* empty_a = full_a + p.na_stages;        // [na]
+  uint64_t* full_b = empty_a + p.na_stages;        // [nb]
+  uint64_t* empty_b = full_b + p.nb_stages;        // [nb]
+  uint64_t* tmem_full = empty_b + p.nb_stages;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int f0 = blockIdx.x * kTcM;   // first flattened output (m * nsub + w) of this tile
-  const int nt = blockIdx.y;
-  const int bb = blockIdx.z;
-  const int F = p.M * p.nsub;         // flattened outputs per batch item in this phase
+  const int F = p.M * p.nsub;         // flattened outputs (m * nsub + w) per batch item in this phase
+  const int mtiles = (F + kTcM - 1) / kTcM;
+  const int total_tiles = mtiles * p.ntiles * p.batch;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&full_a[s], 128); mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < p.na_stages; ++s) { mbar_init(&full_a[s], 128); mbar_init(&empty_a[s], 1); }
     for (int s = 0; s < p.nb_stages; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
     mbar_fence_init();
     fence_proxy_async();
   }
@@ -122,141 +125,164 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
+  const uint32_t buf_cols = (uint32_t)(p.tmem_cols / 2);
 
   if (warp < 4) {
     // ===================== activation producers =====================
     int it = 0;
-    for (int c = 0; c < p.kchunks; ++c) {
-      for (int g = 0; g < p.ngroups; ++g, ++it) {
-        const int s = it & 1;
-        mbar_wait(&empty_a[s], ((it >> 1) & 1) ^ 1);
-        uint8_t* img_hi = a_base + s * a_stage_bytes;
-        RowMap rm;
-        rm.base_row = (long long)bb * p.t_in * p.nsub;
-        rm.fv0 = f0 + p.grp_qlo[g] * p.nsub;
-        rm.nsub = p.nsub; rm.step = p.i_step; rm.rho = p.grp_rho[g]; rm.up = p.up; rm.t_lim = p.t_in * p.up;
-        stage_rows<5>(img_hi, img_hi + img_bytes, p.in, p.in.p, p.in.aux, p.c_in, c * kTcKC, rm, p.rows, tid);
-        fence_proxy_async();
-        mbar_arrive(&full_a[s]);
-      }
-    }
-
-    // ===================== epilogue =====================
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const int f = f0 + warp * 32 + lane;
-    const bool valid = f < F;
-    const int m = valid ? (p.nsub == 1 ? f : f / p.nsub) : 0;
-    const int w = valid ? f - m * p.nsub : 0;
-    const int to = p.o_off + p.o_step * m;
-    const long long obase = (((long long)bb * p.t_out + to) * p.nsub + w) * p.c_out + (long long)nt * p.NT;
-    const uint32_t t_lane = tmem_acc + ((uint32_t)(warp * 32) << 16);
-    for (int n0 = 0; n0 < p.NT; n0 += 32) {
-      uint32_t rr[32];
-      if (p.NT - n0 >= 32) {
-        tmem_ld32(t_lane + (uint32_t)n0, rr);
-      } else {  // NT % 32 == 16
-        uint32_t r16[16];
-        tmem_ld16(t_lane + (uint32_t)n0, r16);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) { rr[e] = r16[e]; rr[16 + e] = 0u; }
-      }
-      tmem_ld_wait();
-      if (valid) {
-        const int ncols = min(32, p.NT - n0);
-        for (int e = 0; e < ncols; e += 4) {
-          const long long o = obase + n0 + e;
-          float v[4] = {__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3])};
-          if (p.bias) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nt * p.NT + n0 + e));
-            v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-          }
-          if (p.out_act == KT_ACT_LRELU) {
-#pragma unroll
-            for (int z = 0; z < 4; ++z) v[z] = v[z] > 0.f ? v[z] : v[z] * p.out_slope;
-          } else if (p.out_act == KT_ACT_TANH) {
-#pragma unroll
-            for (int z = 0; z < 4; ++z) v[z] = tanhf(v[z]);
-          }
-          if (p.mask.p) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(p.mask.p + o));
-            v[0] = side_apply(v[0], a.x, p.mask.mode, p.mask.slope);
-            v[1] = side_apply(v[1], a.y, p.mask.mode, p.mask.slope);
-            v[2] = side_apply(v[2], a.z, p.mask.mode, p.mask.slope);
-            v[3] = side_apply(v[3], a.w, p.mask.mode, p.mask.slope);
-          }
-          if (p.resid) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(p.resid + o));
-            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-          }
-          if (p.accumulate) {
-            const float4 a = *reinterpret_cast<const float4*>(p.out + o);
-            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-          }
-          *reinterpret_cast<float4*>(p.out + o) = make_float4(v[0], v[1], v[2], v[3]);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile % mtiles, bb = tile / (mtiles * p.ntiles);
+      const int f0 = mt * kTcM;
+      for (int c = 0; c < p.kchunks; ++c) {
+        for (int g = 0; g < p.ngroups; ++g, ++it) {
+          const int s = it % p.na_stages;
+          mbar_wait(&empty_a[s], ((it / p.na_stages) & 1) ^ 1);
+          uint8_t* img_hi = a_base + (size_t)s * a_stage_bytes;
+          RowMap rm;
+          rm.base_row = (long long)bb * p.t_in * p.nsub;
+          rm.fv0 = f0 + p.grp_qlo[g] * p.nsub;
+          rm.nsub = p.nsub; rm.step = p.i_step; rm.rho = p.grp_rho[g]; rm.up = p.up; rm.t_lim = p.t_in * p.up;
+          stage_rows<5>(img_hi, img_hi + img_bytes, p.in, p.in.p, p.in.aux, p.c_in, c * kTcKC, rm, p.rows, tid);
+          fence_proxy_async();
+          mbar_arrive(&full_a[s]);
         }
       }
     }
-    tc_fence_before();
   } else if (warp == 4) {
     // ===================== weight stream (bulk async copies) =====================
     if (lane == 0) {
       int it = 0;
-      for (int c = 0; c < p.kchunks; ++c) {
-        for (int n = 0; n < p.ntaps; ++n, ++it) {  // taps are ordered by group: same order as the MMA issuer
-          const int s = it % p.nb_stages;
-          const uint32_t par = ((it / p.nb_stages) & 1) ^ 1;
-          mbar_wait(&empty_b[s], par);
-          const long long block = ((long long)p.tap_j[n] * p.kchunks + c) * p.ntiles + nt;
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + block * (long long)b_stage_bytes;
-          mbar_arrive_expect_tx(&full_b[s], (uint32_t)b_stage_bytes);
-          bulk_g2s(b_base + (size_t)s * b_stage_bytes, src, (uint32_t)b_stage_bytes, &full_b[s]);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = (tile / mtiles) % p.ntiles;
+        for (int c = 0; c < p.kchunks; ++c) {
+          for (int n = 0; n < p.ntaps; ++n, ++it) {  // taps are ordered by group: same order as the MMA issuer
+            const int s = it % p.nb_stages;
+            mbar_wait(&empty_b[s], ((it / p.nb_stages) & 1) ^ 1);
+            const long long block = ((long long)p.tap_j[n] * p.kchunks + c) * p.ntiles + nt;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + block * (long long)b_stage_bytes;
+            mbar_arrive_expect_tx(&full_b[s], (uint32_t)b_stage_bytes);
+            bulk_g2s(b_base + (size_t)s * b_stage_bytes, src, (uint32_t)b_stage_bytes, &full_b[s]);
+          }
         }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kTcM, p.NT, 0, 0);
+      int it_a = 0, it_b = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        const int buf = ti & 1;
+        mbar_wait(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1);   // epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_acc + (uint32_t)buf * buf_cols;
+        uint32_t acc = 0;
+        for (int c = 0; c < p.kchunks; ++c) {
+          for (int g = 0; g < p.ngroups; ++g, ++it_a) {
+            const int sa = it_a % p.na_stages;
+            mbar_wait(&full_a[sa], (it_a / p.na_stages) & 1);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(a_base + (size_t)sa * a_stage_bytes);
+            const uint32_t a_lo = a_hi + (uint32_t)img_bytes;
+            for (int n = p.grp_first[g]; n < p.grp_first[g + 1]; ++n, ++it_b) {
+              const int sb = it_b % p.nb_stages;
+              mbar_wait(&full_b[sb], (it_b / p.nb_stages) & 1);
+              tc_fence_after();
+              const uint32_t b_hi = smem_u32(b_base + (size_t)sb * b_stage_bytes);
+              const uint32_t b_lo = b_hi + (uint32_t)(p.NT * 128);
+              const uint32_t shift = (uint32_t)p.tap_shift[n] * 128u;
+#pragma unroll
+              for (int kk = 0; kk < kTcKC / 16; ++kk) {
+                const uint32_t ko = (uint32_t)kk * 32u;
+                const uint64_t da_hi = smem_desc_sw128(a_hi + shift + ko, 16, 1024, false);
+                const uint64_t da_lo = smem_desc_sw128(a_lo + shift + ko, 16, 1024, false);
+                const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024, false);
+                const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 16, 1024, false);
+                umma_bf16(d_tmem, da_lo, db_hi, idesc, acc);
+                acc = 1;
+                umma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
+                umma_bf16(d_tmem, da_hi, db_hi, idesc, 1);
+              }
+              umma_commit(&empty_b[sb]);
+            }
+            umma_commit(&empty_a[sa]);
+          }
+        }
+        umma_commit(&tmem_full[buf]);
       }
     }
     __syncwarp();
   } else {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kTcM, p.NT, 0, 0);
-      int it_a = 0, it_b = 0;
-      uint32_t acc = 0;
-      for (int c = 0; c < p.kchunks; ++c) {
-        for (int g = 0; g < p.ngroups; ++g, ++it_a) {
-          const int sa = it_a & 1;
-          mbar_wait(&full_a[sa], (it_a >> 1) & 1);
-          tc_fence_after();
-          const uint32_t a_hi = smem_u32(a_base + sa * a_stage_bytes);
-          const uint32_t a_lo = a_hi + (uint32_t)img_bytes;
-          for (int n = p.grp_first[g]; n < p.grp_first[g + 1]; ++n, ++it_b) {
-            const int sb = it_b % p.nb_stages;
-            mbar_wait(&full_b[sb], (it_b / p.nb_stages) & 1);
-            tc_fence_after();
-            const uint32_t b_hi = smem_u32(b_base + (size_t)sb * b_stage_bytes);
-            const uint32_t b_lo = b_hi + (uint32_t)(p.NT * 128);
-            const uint32_t shift = (uint32_t)p.tap_shift[n] * 128u;
+    // ===================== epilogue (warps 6-9; TMEM lane quarter = warp & 3) =====================
+    const int quarter = warp & 3;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      const int mt = tile % mtiles, nt = (tile / mtiles) % p.ntiles, bb = tile / (mtiles * p.ntiles);
+      const int buf = ti & 1;
+      mbar_wait(&tmem_full[buf], (ti >> 1) & 1);
+      tc_fence_after();
+      const int f = mt * kTcM + quarter * 32 + lane;
+      const bool valid = f < F;
+      const int m = valid ? (p.nsub == 1 ? f : f / p.nsub) : 0;
+      const int w = valid ? f - m * p.nsub : 0;
+      const int to = p.o_off + p.o_step * m;
+      const long long obase = (((long long)bb * p.t_out + to) * p.nsub + w) * p.c_out + (long long)nt * p.NT;
+      const uint32_t t_lane = tmem_acc + (uint32_t)buf * buf_cols + ((uint32_t)(quarter * 32) << 16);
+      for (int n0 = 0; n0 < p.NT; n0 += 32) {
+        uint32_t rr[32];
+        if (p.NT - n0 >= 32) {
+          tmem_ld32(t_lane + (uint32_t)n0, rr);
+        } else {  // NT % 32 == 16
+          uint32_t r16[16];
+          tmem_ld16(t_lane + (uint32_t)n0, r16);
 #pragma unroll
-            for (int kk = 0; kk < kTcKC / 16; ++kk) {
-              const uint32_t ko = (uint32_t)kk * 32u;
-              const uint64_t da_hi = smem_desc_sw128(a_hi + shift + ko, 16, 1024, false);
-              const uint64_t da_lo = smem_desc_sw128(a_lo + shift + ko, 16, 1024, false);
-              const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024, false);
-              const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 16, 1024, false);
-              umma_bf16(tmem_acc, da_lo, db_hi, idesc, acc);
-              acc = 1;
-              umma_bf16(tmem_acc, da_hi, db_lo, idesc, 1);
-              umma_bf16(tmem_acc, da_hi, db_hi, idesc, 1);
+          for (int e = 0; e < 16; ++e) { rr[e] = r16[e]; rr[16 + e] = 0u; }
+        }
+        tmem_ld_wait();
+        if (n0 + 32 >= p.NT) {   // last TMEM read of this tile: hand the buffer back to the MMA issuer
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[buf]);
+        }
+        if (valid) {
+          const int ncols = min(32, p.NT - n0);
+          for (int e = 0; e < ncols; e += 4) {
+            const long long o = obase + n0 + e;
+            float v[4] = {__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3])};
+            if (p.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nt * p.NT + n0 + e));
+              v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
             }
-            umma_commit(&empty_b[sb]);
+            if (p.out_act == KT_ACT_LRELU) {
+#pragma unroll
+              for (int z = 0; z < 4; ++z) v[z] = v[z] > 0.f ? v[z] : v[z] * p.out_slope;
+            } else if (p.out_act == KT_ACT_TANH) {
+#pragma unroll
+              for (int z = 0; z < 4; ++z) v[z] = tanhf(v[z]);
+            }
+            if (p.mask.p) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(p.mask.p + o));
+              v[0] = side_apply(v[0], a.x, p.mask.mode, p.mask.slope);
+              v[1] = side_apply(v[1], a.y, p.mask.mode, p.mask.slope);
+              v[2] = side_apply(v[2], a.z, p.mask.mode, p.mask.slope);
+              v[3] = side_apply(v[3], a.w, p.mask.mode, p.mask.slope);
+            }
+            if (p.resid) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(p.resid + o));
+              v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+            }
+            if (p.accumulate) {
+              const float4 a = *reinterpret_cast<const float4*>(p.out + o);
+              v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+            }
+            *reinterpret_cast<float4*>(p.out + o) = make_float4(v[0], v[1], v[2], v[3]);
           }
-          umma_commit(&empty_a[sa]);
         }
       }
-      umma_commit(tmem_full);
     }
-    __syncwarp();
   }
 
+  tc_fence_before();
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
@@ -343,6 +369,15 @@ int tc_pack_weights(const float* w, int taps, int K, int N, int NT, void* out, c
   return KT_OK;
 }
 
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 static int run_tc(TcParams p, const Phase& ph, cudaStream_t st) {
   if (ph.M <= 0) return KT_OK;
   KT_REQUIRE(fill_groups(p, ph, p.nsub), "conv_tc: phase exceeds kernel limits (input step %d)", ph.i_step);
@@ -350,18 +385,22 @@ static int run_tc(TcParams p, const Phase& ph, cudaStream_t st) {
   p.ntiles = p.c_out / p.NT;
   p.tmem_cols = 32;
   while (p.tmem_cols < p.NT) p.tmem_cols <<= 1;
-  const int a_bytes = 2 * 2 * p.rows * 128;
+  p.tmem_cols *= 2;                                   // two accumulator buffers
+  const int a_stage = 2 * p.rows * 128;
   const int b_stage = 2 * p.NT * 128;
-  const int budget = kMaxDynSmem - 1024 /*align slack*/ - a_bytes - 256 /*barriers*/;
-  p.nb_stages = std::min(6, budget / b_stage);
+  const int budget = kMaxDynSmem - 1024 /*align slack*/ - 256 /*barriers*/;
+  p.na_stages = 3;
+  if (3 * a_stage + 3 * b_stage > budget) p.na_stages = 2;
+  p.nb_stages = std::min(6, (budget - p.na_stages * a_stage) / b_stage);
   KT_REQUIRE(p.nb_stages >= 2, "conv_tc: shared memory budget exceeded (rows=%d NT=%d)", p.rows, p.NT);
-  const size_t smem = 1024 + a_bytes + (size_t)p.nb_stages * b_stage + 256;
+  const size_t smem = 1024 + (size_t)p.na_stages * a_stage + (size_t)p.nb_stages * b_stage + 256;
   static std::atomic<bool> cfg{false};
   if (!cfg.load(std::memory_order_acquire)) {
     KT_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     cfg.store(true, std::memory_order_release);
   }
-  dim3 grid(ceil_div(p.M * p.nsub, kTcM), p.ntiles, p.batch);
+  const long long tiles = (long long)ceil_div(p.M * p.nsub, kTcM) * p.ntiles * p.batch;
+  const int grid = (int)std::min<long long>(tiles, sm_count());
   conv_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
   KT_CHECK_CUDA(cudaGetLastError());
   return KT_OK;
