@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of CUDA-graph replay")
     ap.add_argument("--ncu", action="store_true", help="profiling mode: 1 warm-up + K steps, nothing else (not a bench number)")
     args = ap.parse_args()
 
@@ -212,9 +213,10 @@ def main():
     W = max(3, args.warmup)
 
     torch.manual_seed(1234)                      # identical replicas on every rank (reference RNG stream)
-    model, opt, sched = K.hifigan_model_builder(CONFIG, dev)
+    use_graph = not args.no_graph and not args.ncu
+    model, opt, sched = K.hifigan_model_builder(CONFIG, dev, capturable=use_graph)
     crit = K.criterion_builder(CONFIG, dev)
-    step = K.GanStep(model, opt, sched, crit, CONFIG)
+    step = K.GanStep(model, opt, sched, crit, CONFIG, cuda_graph=use_graph)
     y_h, x_h = synth_batch(B_PER_GPU, 1234 + rank)
     y_h, x_h = y_h.pin_memory(), x_h.pin_memory()
     y_d, x_d = y_h.to(dev), x_h.to(dev)
@@ -235,8 +237,12 @@ def main():
         torch.cuda.profiler.stop()
         print(json.dumps({"ncu_mode": True, "steps": args.steps, "launches": ops.launch_count()}))
         return
-    for _ in range(W):
+    launches_per_step = None
+    for i in range(W + (3 if use_graph else 0)):     # graph mode: W eager steps, 1 capture step, 2 replays
+        l0 = ops.launch_count()
         log = step.step((y_d, x_d))
+        if ops.launch_count() > l0:
+            launches_per_step = ops.launch_count() - l0   # kernels issued by one (eager / captured) step
     barrier()
 
     # ---- timed region 1: inputs resident in HBM ----
@@ -253,7 +259,7 @@ def main():
     barrier()
     sampler.stop_flag = True
     ms = e0.elapsed_time(e1)
-    launches = ops.launch_count() - n0 + args.steps
+    launches = (ops.launch_count() - n0 + args.steps) if not use_graph else (launches_per_step + 1) * args.steps
     t_ms = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -265,9 +271,12 @@ def main():
     e0.record()
     for _ in range(args.steps):
         flush.zero_()
-        yb = y_h.to(dev, non_blocking=True)
-        xb = x_h.to(dev, non_blocking=True)
-        log = step.step((yb, xb))
+        if use_graph:
+            log = step.step((y_h, x_h))               # pinned host -> the graph's static input buffers (H2D inside)
+        else:
+            yb = y_h.to(dev, non_blocking=True)
+            xb = x_h.to(dev, non_blocking=True)
+            log = step.step((yb, xb))
         g_loss = float(log["generator_loss"])     # D2H read of the step's result
         d_loss = float(log["discriminator_loss"])
     e1.record()
@@ -285,6 +294,7 @@ def main():
         "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "segment": T_WAV, "parallelism": f"dp{world}",
                    "precision": "fp32 storage; tcgen05 layers bf16x3 split (fp32-equivalent), others exact fp32 FFMA",
                    "l2": "explicit 256 MB flush write between timed iterations",
+                   "launch": "3 CUDA graphs per step (replay)" if use_graph else "eager launches",
                    "gflop_per_step_as_reference_executes": FLOP_PER_SAMPLE * B_PER_GPU * T_WAV / 1e9},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": (y_h.numel() + x_h.numel()) * 4,
                 "d2h_bytes_per_step": 8},
@@ -308,8 +318,9 @@ def roofline_leg(step, batch, ops, ms_per_step):
     """One extra instrumented step: every conv library call is bracketed by CUDA events on the
     launching stream; the dominant kernel class's achieved algorithmic rate is reported against the
     measured peak (MEASURED_PEAKS.json, else the B200_PROFILING.md fallback)."""
+    step.invalidate_weight_caches()        # eager launches after graph replays: prepared weights must be rebuilt
     prof = ops.set_profiler(True)
-    step.step(batch)
+    step._eager_step(*batch)
     summ = prof.summary()
     ops.set_profiler(False)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

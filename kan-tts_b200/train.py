@@ -8,6 +8,11 @@ alter any result:
     the reference computes, all-reduces and then zeroes them (trainer.py:577-578);
   * losses are kept as device tensors; ``.item()`` is only called by ``losses_to_float``.
 
+Launch overhead: one step is ~3000 kernel launches from Python.  ``GanStep(..., cuda_graph=True)``
+captures the step into three CUDA graphs (generator fwd/bwd | generator Adam + discriminator fwd/bwd |
+discriminator Adam), split exactly at the two gradient exchanges, and replays them -- "CUDA streams
+and graphs instead of a tracing compiler".  The captured work is identical to the eager step.
+
 Multi-GPU (one process per GPU, ``torch.distributed`` NCCL over NVLink/NVSwitch): the batch is
 sharded by utterance, replicas are identical, and the only exchange is the gradient all-reduce
 (mean) -- replacing the three DistributedDataParallel wrappers of kantts/models/__init__.py:71-84.
@@ -48,66 +53,80 @@ class GanStep:
     """model = {"generator": G, "discriminator": {name: D}}, optimizer / scheduler dicts of the same
     shape and ``criterion`` as built by the reference's builders (or this package's)."""
 
-    def __init__(self, model, optimizer, scheduler, criterion, config, skip_unused_d_grads=True):
+    def __init__(self, model, optimizer, scheduler, criterion, config, skip_unused_d_grads=True, cuda_graph=False,
+                 graph_warmup=3):
         self.model, self.optimizer, self.scheduler = model, optimizer, scheduler
         self.criterion, self.config = criterion, config
         self.skip_unused_d_grads = skip_unused_d_grads
         self.g_grads = FlatGrads(model["generator"])
         self.d_grads = {k: FlatGrads(m) for k, m in model["discriminator"].items()}
         self.steps = 1
+        self.cuda_graph = cuda_graph
+        self.graph_warmup = graph_warmup
+        self._graphs = None
+        self._eager_done = 0
+        self._static = None
+        self._log = {}
 
-    def step(self, batch):
-        """batch = (y (B,1,T) waveform, x (B,80,T/hop) mel) already on the device -> dict of loss tensors"""
-        y, x = batch
-        cfg, crit, model = self.config, self.criterion, self.model
-        log = {}
-        if self.steps >= cfg.get("generator_train_start_steps", 0):
-            y_ = model["generator"](x)
-            gen_loss = 0.0
-            if crit.get("stft_loss", None):
-                sc_loss, mag_loss = crit["stft_loss"](y_, y)
-                gen_loss = gen_loss + (sc_loss + mag_loss) * crit["stft_loss"].weights
-                log["spectral_convergence_loss"], log["log_stft_magnitude_loss"] = sc_loss, mag_loss
-            if crit.get("mel_loss", None):
-                mel_loss = crit["mel_loss"](y_, y)
-                gen_loss = gen_loss + mel_loss * crit["mel_loss"].weights
-                log["mel_loss"] = mel_loss
-            if self.steps > cfg["discriminator_train_start_steps"]:
-                if self.skip_unused_d_grads:
-                    for fg in self.d_grads.values():
-                        fg.set_requires_grad(False)
-                adv_loss = 0.0
-                fmap_lst_ = []
+    # ---- the three segments (split at the two gradient exchanges) -----------------------------------------
+    def _g_active(self):
+        return self.steps >= self.config.get("generator_train_start_steps", 0)
+
+    def _d_active(self):
+        return self.steps > self.config["discriminator_train_start_steps"]
+
+    def _seg_generator(self, y, x):
+        """generator forward, losses, backward (trainer.py:473-546)"""
+        cfg, crit, model, log = self.config, self.criterion, self.model, self._log
+        y_ = model["generator"](x)
+        gen_loss = 0.0
+        if crit.get("stft_loss", None):
+            sc_loss, mag_loss = crit["stft_loss"](y_, y)
+            gen_loss = gen_loss + (sc_loss + mag_loss) * crit["stft_loss"].weights
+            log["spectral_convergence_loss"], log["log_stft_magnitude_loss"] = sc_loss, mag_loss
+        if crit.get("mel_loss", None):
+            mel_loss = crit["mel_loss"](y_, y)
+            gen_loss = gen_loss + mel_loss * crit["mel_loss"].weights
+            log["mel_loss"] = mel_loss
+        if self._d_active():
+            if self.skip_unused_d_grads:
+                for fg in self.d_grads.values():
+                    fg.set_requires_grad(False)
+            adv_loss = 0.0
+            fmap_lst_ = []
+            for name, disc in model["discriminator"].items():
+                p_, fmap_ = disc(y_)
+                fmap_lst_.append(fmap_)
+                adv_loss = adv_loss + crit["generator_adv_loss"](p_)
+            gen_loss = gen_loss + adv_loss * crit["generator_adv_loss"].weights
+            log["adversarial_loss"] = adv_loss
+            if crit.get("feat_match_loss", None):
+                fmap_lst = []
                 for name, disc in model["discriminator"].items():
-                    p_, fmap_ = disc(y_)
-                    fmap_lst_.append(fmap_)
-                    adv_loss = adv_loss + crit["generator_adv_loss"](p_)
-                gen_loss = gen_loss + adv_loss * crit["generator_adv_loss"].weights
-                log["adversarial_loss"] = adv_loss
-                if crit.get("feat_match_loss", None):
-                    fmap_lst = []
-                    for name, disc in model["discriminator"].items():
-                        with torch.no_grad():
-                            p, fmap = disc(y)
-                            fmap_lst.append(fmap)
-                    fm_loss = 0.0
-                    for fmap_, fmap in zip(fmap_lst, fmap_lst_):          # argument order: trainer.py:535-538
-                        fm_loss = fm_loss + crit["feat_match_loss"](fmap_, fmap)
-                    log["feature_matching_loss"] = fm_loss
-                    gen_loss = gen_loss + fm_loss * crit["feat_match_loss"].weights
-                if self.skip_unused_d_grads:
-                    for fg in self.d_grads.values():
-                        fg.set_requires_grad(True)
-            log["generator_loss"] = gen_loss
-            self.g_grads.zero()
-            gen_loss.backward()
-            self.g_grads.all_reduce_mean()
+                    with torch.no_grad():
+                        p, fmap = disc(y)
+                        fmap_lst.append(fmap)
+                fm_loss = 0.0
+                for fmap_, fmap in zip(fmap_lst, fmap_lst_):          # argument order: trainer.py:535-538
+                    fm_loss = fm_loss + crit["feat_match_loss"](fmap_, fmap)
+                log["feature_matching_loss"] = fm_loss
+                gen_loss = gen_loss + fm_loss * crit["feat_match_loss"].weights
+            if self.skip_unused_d_grads:
+                for fg in self.d_grads.values():
+                    fg.set_requires_grad(True)
+        log["generator_loss"] = gen_loss
+        self.g_grads.zero()
+        gen_loss.backward()
+
+    def _seg_gopt_discriminator(self, y, x):
+        """generator Adam (trainer.py:547-553), then discriminator forward/backward (:556-580)"""
+        cfg, crit, model, log = self.config, self.criterion, self.model, self._log
+        if self._g_active():
             if cfg["generator_grad_norm"] > 0:
                 torch.nn.utils.clip_grad_norm_(model["generator"].parameters(), cfg["generator_grad_norm"])
             self.optimizer["generator"].step()
             self.scheduler["generator"].step()
-
-        if self.steps > cfg["discriminator_train_start_steps"]:
+        if self._d_active():
             with torch.no_grad():
                 y_ = model["generator"](x)
             dis_loss = 0.0
@@ -122,8 +141,11 @@ class GanStep:
             for fg in self.d_grads.values():
                 fg.zero()
             dis_loss.backward()
-            for fg in self.d_grads.values():
-                fg.all_reduce_mean()
+
+    def _seg_dopt(self):
+        """discriminator Adam (trainer.py:581-589)"""
+        cfg, model = self.config, self.model
+        if self._d_active():
             if cfg["discriminator_grad_norm"] > 0:
                 for m in model["discriminator"].values():
                     torch.nn.utils.clip_grad_norm_(m.parameters(), cfg["discriminator_grad_norm"])
@@ -131,8 +153,88 @@ class GanStep:
                 self.optimizer["discriminator"][key].step()
             for key in self.scheduler["discriminator"].keys():
                 self.scheduler["discriminator"][key].step()
+
+    def _eager_step(self, y, x):
+        self._log = {}
+        if self._g_active():
+            self._seg_generator(y, x)
+            self.g_grads.all_reduce_mean()
+        self._seg_gopt_discriminator(y, x)
+        if self._d_active():
+            for fg in self.d_grads.values():
+                fg.all_reduce_mean()
+        self._seg_dopt()
         self.steps += 1
-        return log
+        return dict(self._log)
+
+    def invalidate_weight_caches(self):
+        """Forget every prepared (kernel-layout) weight: needed when eager launches follow graph replays,
+        because replays update parameters without bumping the Python-side tensor versions."""
+        from . import ops
+        mods = [self.model["generator"], *self.model["discriminator"].values()]
+        for m in mods:
+            for sub in m.modules():
+                c = getattr(sub, "_cache", None)
+                if isinstance(c, ops.PreparedWeight):
+                    c.key = None
+
+    # ---- CUDA-graph replay -----------------------------------------------------------------------------------
+    def _capture(self, y, x):
+        if not (self._g_active() and self._d_active()):
+            raise RuntimeError("GanStep(cuda_graph=True): capture needs both phases active (steps >= start steps)")
+        for opt in [self.optimizer["generator"], *self.optimizer["discriminator"].values()]:
+            for grp in opt.param_groups:
+                if not grp.get("capturable", False):
+                    raise RuntimeError("GanStep(cuda_graph=True) needs optimizers built with capturable=True")
+        self._static = (y.clone(), x.clone())
+        sy, sx = self._static
+        self._log = {}
+        torch.cuda.synchronize()
+        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            self._seg_generator(sy, sx)
+        self.g_grads.all_reduce_mean()
+        with torch.cuda.graph(g2, pool=g1.pool()):
+            self._seg_gopt_discriminator(sy, sx)
+        for fg in self.d_grads.values():
+            fg.all_reduce_mean()
+        with torch.cuda.graph(g3, pool=g1.pool()):
+            self._seg_dopt()
+        self._graphs = (g1, g2, g3)
+        self.steps += 1        # the capture pass executed one real step
+        return dict(self._log)
+
+    def _replay(self, y, x):
+        sy, sx = self._static
+        sy.copy_(y, non_blocking=True)
+        sx.copy_(x, non_blocking=True)
+        g1, g2, g3 = self._graphs
+        g1.replay()
+        self.g_grads.all_reduce_mean()
+        g2.replay()
+        for fg in self.d_grads.values():
+            fg.all_reduce_mean()
+        g3.replay()
+        self.steps += 1
+        return dict(self._log)
+
+    def step(self, batch):
+        """batch = (y (B,1,T) waveform, x (B,80,T/hop) mel) on the device -> dict of loss tensors"""
+        y, x = batch
+        if not self.cuda_graph:
+            return self._eager_step(y, x)
+        if self._graphs is not None:
+            return self._replay(y, x)
+        if self._eager_done < self.graph_warmup:
+            # eager warm-up on a side stream (allocator / Adam state / one-time CUDA attribute calls settle)
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                out = self._eager_step(y, x)
+            torch.cuda.current_stream().wait_stream(s)
+            self._eager_done += 1
+            return out
+        return self._capture(y, x)
 
 
 def losses_to_float(log):
@@ -144,9 +246,10 @@ def optimizer_builder(model_params, opt_name, opt_params):
     return getattr(torch.optim, opt_name)(model_params, **opt_params)
 
 
-def hifigan_model_builder(config, device):
+def hifigan_model_builder(config, device, capturable=False):
     """kantts/models/__init__.py:28-86 without the DDP wrappers (GanStep reduces the flat gradient
-    buffers itself); scheduler = torch MultiStepLR as in the shipped yamls."""
+    buffers itself); scheduler = torch MultiStepLR as in the shipped yamls.  ``capturable=True`` builds
+    the Adam optimizers so that ``GanStep(cuda_graph=True)`` can capture their step."""
     from . import hifigan
     model = {"discriminator": {}}
     optimizer = {"discriminator": {}}
@@ -156,7 +259,10 @@ def hifigan_model_builder(config, device):
             m = hifigan.Generator(**sect["params"]).to(device)
         else:
             m = getattr(hifigan, name)(**sect["params"]).to(device)
-        opt = optimizer_builder(m.parameters(), sect["optimizer"].get("type", "Adam"), sect["optimizer"].get("params", {}))
+        oparams = dict(sect["optimizer"].get("params", {}))
+        if capturable:
+            oparams["capturable"] = True
+        opt = optimizer_builder(m.parameters(), sect["optimizer"].get("type", "Adam"), oparams)
         sch_t = sect["scheduler"].get("type", "StepLR")
         sch = getattr(torch.optim.lr_scheduler, sch_t)(opt, **sect["scheduler"].get("params", {}))
         if name == "Generator":
