@@ -116,14 +116,17 @@ int kt_conv1d_bwd_weight(const KtConv1dDesc* d, const float* x, const float* dy,
                          float* dw, float* dbias, void* stream);
 
 /* ---- tcgen05 (5th-gen tensor core) path: bf16x3 split-precision implicit GEMM, fp32 accumulation in TMEM ----
- * kt_conv1d_tc_plan: returns the output-channel tile NT (> 0) when direction `dir` (0 forward, 1 data
- * gradient) of the layer can run on the tcgen05 kernel (groups 1, contraction channels % 64 == 0,
- * produced channels % 16 == 0, unit input step), else 0.
- * kt_weight_pack_tc: fp32 kernel-layout weights W[taps][K][N] (w_fwd for dir 0, w_bwd for dir 1) ->
- * hi/lo bf16 SWIZZLE_128B tiles ([taps][K/64][N/NT][2][NT][64] bf16, i.e. taps*K*N*4 bytes).
+ * kt_conv1d_tc_plan: returns the (padded) output-channel tile NT > 0 when direction `dir` (0 forward, 1 data
+ * gradient) of the layer can run on the tcgen05 kernel, else 0.  Any stride / period / group count /
+ * channel count qualifies (channels are zero-padded to 64-wide K chunks and 16-wide N tiles; a grouped
+ * conv maps one group to one N tile); only the nearest-upsampled data gradient stays on the FFMA path.
+ * kt_conv1d_tc_image_bytes / kt_weight_pack_tc: size of, and packing into, the hi/lo bf16 SWIZZLE_128B
+ * weight tiles ([taps][ceil(K/64)][N tiles][hi|lo][NT][64] bf16) from the fp32 kernel-layout weight of
+ * that direction (w_fwd for dir 0, w_bwd for dir 1).
  * kt_conv1d_{fwd,bwd_data}_tc: same contract as the fp32 entry points, `wimg` = the packed tiles. */
 int kt_conv1d_tc_plan(const KtConv1dDesc* d, int32_t dir);
-int kt_weight_pack_tc(const float* w, int32_t taps, int32_t k_dim, int32_t n_dim, int32_t n_tile, void* out, void* stream);
+int64_t kt_conv1d_tc_image_bytes(const KtConv1dDesc* d, int32_t dir);
+int kt_weight_pack_tc(const KtConv1dDesc* d, int32_t dir, const float* w, void* out, void* stream);
 int kt_conv1d_fwd_tc(const KtConv1dDesc* d, const float* x, const void* wimg, const float* bias, const float* resid,
                      float* y, void* stream);
 int kt_conv1d_bwd_data_tc(const KtConv1dDesc* d, const float* dy, const float* y, const void* wimg, const float* x,

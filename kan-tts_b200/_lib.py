@@ -55,7 +55,8 @@ PROTOTYPES = {
     "kt_stft_mel_bwd": [ctypes.POINTER(KtMelDesc), _P, _P, _P, _P, _P, _P, _P],
     "kt_l1_sum": [_P, _P, _L, _F, _P, _P],
     "kt_conv1d_tc_plan": [ctypes.POINTER(KtConv1dDesc), _I],
-    "kt_weight_pack_tc": [_P, _I, _I, _I, _I, _P, _P],
+    "kt_conv1d_tc_image_bytes": [ctypes.POINTER(KtConv1dDesc), _I],
+    "kt_weight_pack_tc": [ctypes.POINTER(KtConv1dDesc), _I, _P, _P, _P],
     "kt_conv1d_fwd_tc": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P],
     "kt_conv1d_bwd_data_tc": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P],
     "kt_conv1d_bwd_weight_tc_workspace": [ctypes.POINTER(KtConv1dDesc)],
@@ -103,7 +104,7 @@ def load():
     for name, argtypes in PROTOTYPES.items():
         fn = getattr(lib, name)            # AttributeError here = header / library mismatch
         fn.argtypes = argtypes
-        fn.restype = ctypes.c_int64 if name.endswith("_workspace") else ctypes.c_int
+        fn.restype = ctypes.c_int64 if name.endswith(("_workspace", "_bytes")) else ctypes.c_int
     lib.kt_last_error.argtypes = []
     lib.kt_last_error.restype = ctypes.c_char_p
     _lib = lib

@@ -20,7 +20,8 @@ int stft_mel_bwd(const KtMelDesc*, const float*, const float*, const float*, con
 long long wgrad_tc_workspace(const KtConv1dDesc*);
 int conv1d_bwd_weight_tc(const KtConv1dDesc*, const float*, const float*, const float*, float*, float*, float*, long long, cudaStream_t);
 int tc_plan(const KtConv1dDesc*, int);
-int tc_pack_weights(const float*, int, int, int, int, void*, cudaStream_t);
+long long tc_image_bytes(const KtConv1dDesc*, int);
+int tc_pack_layer(const KtConv1dDesc*, int, const float*, void*, cudaStream_t);
 int conv1d_fwd_tc(const KtConv1dDesc*, const float*, const void*, const float*, const float*, float*, cudaStream_t);
 int conv1d_bwd_data_tc(const KtConv1dDesc*, const float*, const float*, const void*, const float*, float*, cudaStream_t);
 }  // namespace kt
@@ -95,8 +96,14 @@ int kt_conv1d_tc_plan(const KtConv1dDesc* d, int32_t dir) {
   if (kt::validate_conv(d)) return 0;
   return kt::tc_plan(d, dir);
 }
-int kt_weight_pack_tc(const float* w, int32_t taps, int32_t k_dim, int32_t n_dim, int32_t n_tile, void* out, void* stream) {
-  return kt::tc_pack_weights(w, taps, k_dim, n_dim, n_tile, out, ST(stream));
+int64_t kt_conv1d_tc_image_bytes(const KtConv1dDesc* d, int32_t dir) {
+  if (kt::validate_conv(d)) return 0;
+  return kt::tc_image_bytes(d, dir);
+}
+int kt_weight_pack_tc(const KtConv1dDesc* d, int32_t dir, const float* w, void* out, void* stream) {
+  int rc = kt::validate_conv(d);
+  if (rc) return rc;
+  return kt::tc_pack_layer(d, dir, w, out, ST(stream));
 }
 int kt_conv1d_fwd_tc(const KtConv1dDesc* d, const float* x, const void* wimg, const float* bias, const float* resid,
                      float* y, void* stream) {

@@ -40,19 +40,27 @@ constexpr int kTcMaxGroups = 8;  // residue classes (= input step) per phase
 // weight packing: fp32 W[taps][K][N] (kernel layout of conv_ffma.cu) -> bf16 hi/lo SWIZZLE_128B tiles
 //   block (j, kc, nt) = [hi tile | lo tile], tile = NT rows (n) x 64 (k) bf16, row = 128 bytes
 // ---------------------------------------------------------------------------------------------
-__global__ void tc_pack_weights_kernel(const float* __restrict__ w, int taps, int K, int N, int NT,
-                                       __nv_bfloat16* __restrict__ out) {
-  const int kchunks = K / kTcKC, ntiles = N / NT;
-  const long long total = (long long)taps * K * N;
+// K (contraction rows of W) is zero-padded to a multiple of 64 and every N tile to NT rows, so thin
+// (C_in = 1, 32, 80, ...), single-output and GROUPED layers use the same kernel: tile nt covers the
+// columns [nt * n_stride, nt * n_stride + min(n_stride, N - nt * n_stride)) of W (n_stride = NT for a
+// dense layer, C_out / groups for a grouped one, whose W already has K = C_in / groups rows).
+__global__ void tc_pack_weights_kernel(const float* __restrict__ w, int taps, int K, int N, int NT, int n_stride,
+                                       int ntiles, __nv_bfloat16* __restrict__ out) {
+  const int kchunks = (K + kTcKC - 1) / kTcKC;
+  const long long total = (long long)taps * kchunks * ntiles * NT * kTcKC;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int n = (int)(i % N);
-    const int k = (int)((i / N) % K);
-    const int j = (int)(i / ((long long)N * K));
-    const float x = w[i];
+    const int c = (int)(i % kTcKC);
+    const int r = (int)((i / kTcKC) % NT);
+    const long long block = i / ((long long)kTcKC * NT);
+    const int nt = (int)(block % ntiles);
+    const int kc = (int)((block / ntiles) % kchunks);
+    const int j = (int)(block / ((long long)ntiles * kchunks));
+    const int k = kc * kTcKC + c;
+    const int n = nt * n_stride + r;
+    const bool ok = k < K && r < n_stride && n < N;
+    const float x = ok ? w[((long long)j * K + k) * N + n] : 0.f;
     const __nv_bfloat16 hi = __float2bfloat16_rn(x);
     const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-    const int kc = k / kTcKC, c = k % kTcKC, nt = n / NT, r = n % NT;
-    const long long block = ((long long)j * kchunks + kc) * ntiles + nt;
     const long long base = block * (2LL * NT * kTcKC);
     const uint32_t off = (sw128_offset((uint32_t)r, (uint32_t)(c >> 3)) >> 1) + (uint32_t)(c & 7);
     out[base + off] = hi;
@@ -74,6 +82,9 @@ struct TcParams {
   int out_act;
   float out_slope;
   int NT, ntiles, kchunks, rows, na_stages, nb_stages, tmem_cols;
+  int kg;        // contraction channels per tile (C_in, or C_in / groups)
+  int grouped;   // 1: N tile nt = group nt (input channels [nt * kg, +kg), outputs [nt * n_stride, +n_stride))
+  int n_stride;  // output channels advanced per N tile
   // phase: out[(o_off + o_step*m), w] = sum_n W[tap_j[n]] in[(m + q_n)*i_step + rho_n, w]
   int M, o_off, o_step, i_step, up, accumulate;
   int ngroups;                        // residue classes actually used
@@ -132,6 +143,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = tile % mtiles, bb = tile / (mtiles * p.ntiles);
+      const int ch_base = p.grouped ? ((tile / mtiles) % p.ntiles) * p.kg : 0;
       const int f0 = mt * kTcM;
       for (int c = 0; c < p.kchunks; ++c) {
         for (int g = 0; g < p.ngroups; ++g, ++it) {
@@ -142,7 +154,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           rm.base_row = (long long)bb * p.t_in * p.nsub;
           rm.fv0 = f0 + p.grp_qlo[g] * p.nsub;
           rm.nsub = p.nsub; rm.step = p.i_step; rm.rho = p.grp_rho[g]; rm.up = p.up; rm.t_lim = p.t_in * p.up;
-          stage_rows<5>(img_hi, img_hi + img_bytes, p.in, p.in.p, p.in.aux, p.c_in, c * kTcKC, rm, p.rows, tid);
+          stage_rows<5>(img_hi, img_hi + img_bytes, p.in, p.in.p, p.in.aux, p.c_in, ch_base + c * kTcKC,
+                        min(kTcKC, p.kg - c * kTcKC), false, rm, p.rows, tid);
           fence_proxy_async();
           mbar_arrive(&full_a[s]);
         }
@@ -179,6 +192,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         const uint32_t d_tmem = tmem_acc + (uint32_t)buf * buf_cols;
         uint32_t acc = 0;
         for (int c = 0; c < p.kchunks; ++c) {
+          const int kslices = (min(kTcKC, p.kg - c * kTcKC) + 15) >> 4;   // K = 16 slices holding real channels
           for (int g = 0; g < p.ngroups; ++g, ++it_a) {
             const int sa = it_a % p.na_stages;
             mbar_wait(&full_a[sa], (it_a / p.na_stages) & 1);
@@ -192,8 +206,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
               const uint32_t b_hi = smem_u32(b_base + (size_t)sb * b_stage_bytes);
               const uint32_t b_lo = b_hi + (uint32_t)(p.NT * 128);
               const uint32_t shift = (uint32_t)p.tap_shift[n] * 128u;
-#pragma unroll
-              for (int kk = 0; kk < kTcKC / 16; ++kk) {
+              for (int kk = 0; kk < kslices; ++kk) {
                 const uint32_t ko = (uint32_t)kk * 32u;
                 const uint64_t da_hi = smem_desc_sw128(a_hi + shift + ko, 16, 1024, false);
                 const uint64_t da_lo = smem_desc_sw128(a_lo + shift + ko, 16, 1024, false);
@@ -227,7 +240,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       const int m = valid ? (p.nsub == 1 ? f : f / p.nsub) : 0;
       const int w = valid ? f - m * p.nsub : 0;
       const int to = p.o_off + p.o_step * m;
-      const long long obase = (((long long)bb * p.t_out + to) * p.nsub + w) * p.c_out + (long long)nt * p.NT;
+      const long long obase = (((long long)bb * p.t_out + to) * p.nsub + w) * p.c_out + (long long)nt * p.n_stride;
+      const int n_valid = min(p.n_stride, p.c_out - nt * p.n_stride);   // real output channels of this tile
+      const bool vec_out = ((n_valid | p.c_out | p.n_stride) & 3) == 0;
       const uint32_t t_lane = tmem_acc + (uint32_t)buf * buf_cols + ((uint32_t)(quarter * 32) << 16);
       for (int n0 = 0; n0 < p.NT; n0 += 32) {
         uint32_t rr[32];
@@ -244,13 +259,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           tc_fence_before();
           mbar_arrive(&tmem_empty[buf]);
         }
-        if (valid) {
-          const int ncols = min(32, p.NT - n0);
+        if (valid && !vec_out) {
+          // thin / unaligned tiles (C_out = 1, ...): scalar epilogue
+          const int ncols = min(32, n_valid - n0);
+          for (int e = 0; e < ncols; ++e) {
+            const long long o = obase + n0 + e;
+            float v = __uint_as_float(rr[e]);
+            if (p.bias) v += __ldg(p.bias + nt * p.n_stride + n0 + e);
+            if (p.out_act == KT_ACT_LRELU) v = v > 0.f ? v : v * p.out_slope;
+            else if (p.out_act == KT_ACT_TANH) v = tanhf(v);
+            if (p.mask.p) v = side_apply(v, __ldg(p.mask.p + o), p.mask.mode, p.mask.slope);
+            if (p.resid) v += __ldg(p.resid + o);
+            if (p.accumulate) v += p.out[o];
+            p.out[o] = v;
+          }
+        } else if (valid) {
+          const int ncols = min(32, n_valid - n0);
           for (int e = 0; e < ncols; e += 4) {
             const long long o = obase + n0 + e;
             float v[4] = {__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3])};
             if (p.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nt * p.NT + n0 + e));
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nt * p.n_stride + n0 + e));
               v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
             }
             if (p.out_act == KT_ACT_LRELU) {
@@ -293,12 +322,44 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int pick_nt(int n) {
-  if (n % 16 != 0) return 0;
-  if (n <= 256) return n;
-  if (n % 256 == 0) return 256;
-  if (n % 128 == 0) return 128;
-  return 0;
+// Layer-level tiling of one direction (0 forward, 1 data gradient).
+struct TcLayerPlan {
+  bool ok;
+  int kg;        // contraction channels per tile
+  int n_total;   // produced channels (tensor width)
+  int n_stride;  // produced channels per N tile
+  int NT;        // padded N tile (multiple of 16, <= 256)
+  int ntiles, kchunks, grouped;
+};
+
+static TcLayerPlan layer_plan(const KtConv1dDesc* d, int dir) {
+  TcLayerPlan L{};
+  const int g = d->groups;
+  const int kin = (dir == 0 ? d->c_in : d->c_out) / g;     // contraction channels per group
+  const int pout = (dir == 0 ? d->c_out : d->c_in) / g;    // produced channels per group
+  L.kg = kin;
+  L.n_total = pout * g;
+  L.kchunks = ceil_div(kin, kTcKC);
+  L.grouped = g > 1;
+  if (g > 1) {
+    if (pout > 256) return L;
+    L.n_stride = pout; L.NT = (pout + 15) & ~15; L.ntiles = g;
+  } else if (pout <= 256) {
+    L.n_stride = pout; L.NT = (pout + 15) & ~15; L.ntiles = 1;
+    // under-filled grids (short sequences x wide layers): split N so that >= ~1 tile per SM exists
+    const long long mtiles = (long long)ceil_div((dir == 0 ? d->t_out : d->t_in) * d->nsub, kTcM) * d->batch;
+    while (mtiles * L.ntiles < 120 && L.NT >= 128 && L.NT % 32 == 0 && pout % (L.NT / 2) == 0) {
+      L.NT /= 2; L.n_stride = L.NT; L.ntiles = pout / L.NT;
+    }
+  } else {
+    L.NT = pout % 256 == 0 ? 256 : (pout % 128 == 0 ? 128 : 0);
+    if (L.NT == 0) return L;
+    const long long mtiles = (long long)ceil_div((dir == 0 ? d->t_out : d->t_in) * d->nsub, kTcM) * d->batch;
+    if (L.NT == 256 && mtiles * (pout / 256) < 120) L.NT = 128;
+    L.n_stride = L.NT; L.ntiles = pout / L.NT;
+  }
+  L.ok = true;
+  return L;
 }
 
 std::vector<Phase> conv_phases(const KtConv1dDesc* d, int dir);  // conv_ffma.cu
@@ -346,25 +407,30 @@ static bool fill_groups(TcParams& p, const Phase& ph, int nsub) {
 
 // Is (direction dir: 0 fwd, 1 bwd_data) of this layer runnable on the tcgen05 kernel?  -> N tile or 0
 int tc_plan(const KtConv1dDesc* d, int dir) {
-  if (d->groups != 1) return 0;
   if (dir == 1 && d->upsample > 1) return 0;          // `upsample` single-tap residue phases: staging-bound, stays FFMA
-  const int cin = dir == 0 ? d->c_in : d->c_out;     // contraction channels
-  const int cout = dir == 0 ? d->c_out : d->c_in;    // produced channels
-  if (cin % kTcKC != 0) return 0;
-  const int nt = pick_nt(cout);
-  if (nt == 0) return 0;
+  const TcLayerPlan L = layer_plan(d, dir);
+  if (!L.ok) return 0;
   TcParams p{};
   for (const Phase& ph : conv_phases(d, dir))
     if (!fill_groups(p, ph, d->nsub)) return 0;
-  return nt;
+  return L.NT;
 }
 
-int tc_pack_weights(const float* w, int taps, int K, int N, int NT, void* out, cudaStream_t st) {
-  KT_REQUIRE(w && out && taps > 0 && K % kTcKC == 0 && NT > 0 && N % NT == 0 && NT % 16 == 0 && NT <= 256,
-             "tc_pack_weights: bad shape taps=%d K=%d N=%d NT=%d", taps, K, N, NT);
-  const long long total = (long long)taps * K * N;
+// bytes of the packed split-bf16 weight image of direction `dir` (0 when unsupported)
+long long tc_image_bytes(const KtConv1dDesc* d, int dir) {
+  if (tc_plan(d, dir) == 0) return 0;
+  const TcLayerPlan L = layer_plan(d, dir);
+  return (long long)d->kernel * L.kchunks * L.ntiles * 2LL * L.NT * kTcKC * 2LL;
+}
+
+// w = the fp32 kernel-layout weight of this direction (w_fwd for dir 0, w_bwd for dir 1): [taps][K][N]
+int tc_pack_layer(const KtConv1dDesc* d, int dir, const float* w, void* out, cudaStream_t st) {
+  KT_REQUIRE(w && out && tc_plan(d, dir) > 0, "tc_pack_layer: layer not supported by the tcgen05 path");
+  const TcLayerPlan L = layer_plan(d, dir);
+  const long long total = (long long)d->kernel * L.kchunks * L.ntiles * L.NT * kTcKC;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
-  tc_pack_weights_kernel<<<blocks, 256, 0, st>>>(w, taps, K, N, NT, reinterpret_cast<__nv_bfloat16*>(out));
+  tc_pack_weights_kernel<<<blocks, 256, 0, st>>>(w, d->kernel, L.kg, L.n_total, L.NT, L.n_stride, L.ntiles,
+                                                 reinterpret_cast<__nv_bfloat16*>(out));
   KT_CHECK_CUDA(cudaGetLastError());
   return KT_OK;
 }
@@ -381,8 +447,6 @@ static int sm_count() {
 static int run_tc(TcParams p, const Phase& ph, cudaStream_t st) {
   if (ph.M <= 0) return KT_OK;
   KT_REQUIRE(fill_groups(p, ph, p.nsub), "conv_tc: phase exceeds kernel limits (input step %d)", ph.i_step);
-  p.kchunks = p.c_in / kTcKC;
-  p.ntiles = p.c_out / p.NT;
   p.tmem_cols = 32;
   while (p.tmem_cols < p.NT) p.tmem_cols <<= 1;
   p.tmem_cols *= 2;                                   // two accumulator buffers
@@ -416,14 +480,15 @@ static Side make_side_tc(const float* p, const float* aux, int act, float slope,
 
 int conv1d_fwd_tc(const KtConv1dDesc* d, const float* x, const void* wimg, const float* bias, const float* resid,
                   float* y, cudaStream_t st) {
-  const int nt = tc_plan(d, 0);
-  KT_REQUIRE(nt > 0, "conv1d_fwd_tc: layer not supported by the tcgen05 path");
+  KT_REQUIRE(tc_plan(d, 0) > 0, "conv1d_fwd_tc: layer not supported by the tcgen05 path");
+  const TcLayerPlan L = layer_plan(d, 0);
   TcParams p{};
+  p.NT = L.NT; p.ntiles = L.ntiles; p.kchunks = L.kchunks; p.kg = L.kg; p.grouped = L.grouped; p.n_stride = L.n_stride;
   p.in = make_side_tc(x, nullptr, d->act_in, d->act_in_slope, false);
   p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
   p.bias = bias; p.resid = resid; p.mask = Side{nullptr, nullptr, 0, 0.f}; p.out = y;
   p.batch = d->batch; p.nsub = d->nsub; p.t_in = d->t_in; p.t_out = d->t_out; p.c_in = d->c_in; p.c_out = d->c_out;
-  p.out_act = d->act_out; p.out_slope = d->act_out_slope; p.NT = nt;
+  p.out_act = d->act_out; p.out_slope = d->act_out_slope;
   for (const Phase& ph : conv_phases(d, 0)) {
     int rc = run_tc(p, ph, st);
     if (rc) return rc;
@@ -433,18 +498,19 @@ int conv1d_fwd_tc(const KtConv1dDesc* d, const float* x, const void* wimg, const
 
 int conv1d_bwd_data_tc(const KtConv1dDesc* d, const float* dy, const float* y, const void* wimg, const float* x,
                        float* dx, cudaStream_t st) {
-  const int nt = tc_plan(d, 1);
-  KT_REQUIRE(nt > 0, "conv1d_bwd_data_tc: layer not supported by the tcgen05 path");
+  KT_REQUIRE(tc_plan(d, 1) > 0, "conv1d_bwd_data_tc: layer not supported by the tcgen05 path");
+  const TcLayerPlan L = layer_plan(d, 1);
   KT_REQUIRE(d->act_out == KT_ACT_NONE || y != nullptr, "bwd_data: y required when act_out != NONE");
   KT_REQUIRE(d->act_in == KT_ACT_NONE || x != nullptr, "bwd_data: x required when act_in != NONE");
   TcParams p{};
+  p.NT = L.NT; p.ntiles = L.ntiles; p.kchunks = L.kchunks; p.kg = L.kg; p.grouped = L.grouped; p.n_stride = L.n_stride;
   p.in = make_side_tc(dy, y, d->act_out, d->act_out_slope, true);
   p.wimg = reinterpret_cast<const __nv_bfloat16*>(wimg);
   p.bias = nullptr; p.resid = nullptr; p.out = dx;
   p.mask = d->act_in == KT_ACT_LRELU ? Side{x, nullptr, SIDE_DLRELU, d->act_in_slope} : Side{nullptr, nullptr, 0, 0.f};
   // roles swap: the gathered tensor is dy (c_out channels, t_out rows), the product is dx
   p.batch = d->batch; p.nsub = d->nsub; p.t_in = d->t_out; p.t_out = d->t_in; p.c_in = d->c_out; p.c_out = d->c_in;
-  p.out_act = KT_ACT_NONE; p.out_slope = 0.f; p.NT = nt;
+  p.out_act = KT_ACT_NONE; p.out_slope = 0.f;
   for (const Phase& ph : conv_phases(d, 1)) {
     int rc = run_tc(p, ph, st);
     if (rc) return rc;

@@ -185,9 +185,16 @@ struct RowMap {
 
 template <int NB>
 __device__ __forceinline__ void stage_rows(uint8_t* img_hi, uint8_t* img_lo, const Side& s, const float* base,
-                                           const float* aux_base, int c_total, int ch0, const RowMap& rm, int rows,
-                                           int tid) {
+                                           const float* aux_base, int c_total, int ch0, int c_valid, bool fill_all,
+                                           const RowMap& rm, int rows, int tid) {
+  // c_valid (1..64) = real channels of this 64-wide chunk; the rest of the image row is zero padding
+  // (thin / grouped layers).  When channels are the K dimension (forward / dgrad) the 16-byte chunks past
+  // the last K = 16 slice the MMA reads need not be written (fill_all = false); when channels are the
+  // M / N dimension (weight gradient) every chunk of the row is read and must be zero-filled.
   const int q = tid & 7;
+  if (!fill_all && q * 8 >= ((c_valid + 15) & ~15)) return;
+  const int nv = min(8, c_valid - q * 8);                       // valid channels of this thread's chunk (may be <= 0)
+  const bool vec = nv == 8 && (c_total & 3) == 0 && ((ch0 + q * 8) & 3) == 0;
   const bool has_aux = s.mode >= SIDE_DLRELU;
   for (int r0 = tid >> 3; r0 < rows; r0 += 16 * NB) {
     float4 v[NB][2], a[NB][2];
@@ -195,13 +202,25 @@ __device__ __forceinline__ void stage_rows(uint8_t* img_hi, uint8_t* img_lo, con
     for (int i = 0; i < NB; ++i) {
       const int r = r0 + 16 * i;
       long long srow = 0;
-      const bool ok = r < rows && rm.map(r, srow);
+      const bool ok = r < rows && nv > 0 && rm.map(r, srow);
       const long long off = ok ? srow * c_total + ch0 + q * 8 : 0;
-      v[i][0] = ok ? __ldg(reinterpret_cast<const float4*>(base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      v[i][1] = ok ? __ldg(reinterpret_cast<const float4*>(base + off + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (has_aux) {
-        a[i][0] = ok ? __ldg(reinterpret_cast<const float4*>(aux_base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        a[i][1] = ok ? __ldg(reinterpret_cast<const float4*>(aux_base + off + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vec) {
+        v[i][0] = ok ? __ldg(reinterpret_cast<const float4*>(base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[i][1] = ok ? __ldg(reinterpret_cast<const float4*>(base + off + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_aux) {
+          a[i][0] = ok ? __ldg(reinterpret_cast<const float4*>(aux_base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          a[i][1] = ok ? __ldg(reinterpret_cast<const float4*>(aux_base + off + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      } else {
+        float t[8], u[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const bool oe = ok && e < nv;
+          t[e] = oe ? __ldg(base + off + e) : 0.f;
+          u[e] = (oe && has_aux) ? __ldg(aux_base + off + e) : 0.f;
+        }
+        v[i][0] = make_float4(t[0], t[1], t[2], t[3]); v[i][1] = make_float4(t[4], t[5], t[6], t[7]);
+        a[i][0] = make_float4(u[0], u[1], u[2], u[3]); a[i][1] = make_float4(u[4], u[5], u[6], u[7]);
       }
     }
 #pragma unroll

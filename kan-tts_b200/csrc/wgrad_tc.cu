@@ -33,7 +33,8 @@ constexpr int kWgMaxGroups = 24;
 struct WgTcParams {
   Side a, b;
   float* ws;
-  int batch, nsub, t_a, t_b, ca, cb, taps_total;
+  int batch, nsub, t_a, t_b, ca, cb, taps_total;   // ca / cb = tensor widths (all groups)
+  int groups, ca_g, cb_g;                           // channels per group (= ca, cb when groups == 1)
   int M;                       // base rows m per sub-sequence
   int step, up;
   int mode, NT, n_cb_tiles, n_ca_tiles;
@@ -64,8 +65,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ca_tile = blockIdx.x / p.n_cb_tiles;
   const int cb_tile = blockIdx.x % p.n_cb_tiles;
+  const int ca_tile = (blockIdx.x / p.n_cb_tiles) % p.n_ca_tiles;
+  const int cgrp = blockIdx.x / (p.n_cb_tiles * p.n_ca_tiles);   // conv group
   const int grp = blockIdx.y;
   const int u0 = p.grp_first_unit[grp];
   const int nu = p.grp_first_unit[grp + 1] - u0;
@@ -103,7 +105,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       ra.nsub = p.nsub; ra.step = p.step; ra.rho = p.grp_rho[grp]; ra.up = p.up; ra.t_lim = p.t_a * p.up;
       for (int g = 0; g < p.a_groups; ++g) {
         uint8_t* hi = st + (size_t)g * 2 * img_a;
-        stage_rows<5>(hi, hi + img_a, p.a, p.a.p, p.a.aux, p.ca, ca_tile * (p.mode == 0 ? 128 : 64) + g * 64, ra, p.rows_a, tid);
+        const int c_lo = ca_tile * (p.mode == 0 ? 128 : 64) + g * 64;           // channel offset inside the group
+        stage_rows<5>(hi, hi + img_a, p.a, p.a.p, p.a.aux, p.ca, cgrp * p.ca_g + c_lo, min(64, p.ca_g - c_lo), true, ra,
+                      p.rows_a, tid);
       }
       RowMap rb;  // base side: rows m (flattened with w), zero beyond M
       rb.base_row = (long long)bb * p.t_b * p.nsub;
@@ -111,7 +115,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       uint8_t* bst = st + (size_t)p.a_groups * 2 * img_a;
       for (int g = 0; g < p.b_groups; ++g) {
         uint8_t* hi = bst + (size_t)g * 2 * img_b;
-        stage_rows<4>(hi, hi + img_b, p.b, p.b.p, p.b.aux, p.cb, cb_tile * p.NT + g * 64, rb, kWgTK, tid);
+        const int c_lo = cb_tile * p.NT + g * 64;
+        stage_rows<4>(hi, hi + img_b, p.b, p.b.p, p.b.aux, p.cb, cgrp * p.cb_g + c_lo, min(64, p.cb_g - c_lo), true, rb,
+                      kWgTK, tid);
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);
@@ -127,16 +133,24 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       bool valid;
       if (p.mode == 0) { tap_n = p.unit_tap0[u0 + u]; ca_idx = ca_tile * 128 + row; valid = true; }
       else { tap_n = p.unit_tap0[u0 + u] + (row >> 6); ca_idx = row & 63; valid = (row >> 6) < p.unit_ntaps[u0 + u]; }
-      const long long obase = valid ? (((long long)split * p.taps_total + p.tap_j[tap_n]) * p.ca + ca_idx) * p.cb + (long long)cb_tile * p.NT : 0;
+      valid = valid && ca_idx < p.ca_g;
+      const int col0 = cb_tile * p.NT;                                    // first column inside the group
+      const long long obase = valid ? (((long long)split * p.taps_total + p.tap_j[tap_n]) * p.ca_g + ca_idx) * p.cb +
+                                          (long long)cgrp * p.cb_g + col0 : 0;
+      const bool vec = ((p.cb | p.cb_g) & 3) == 0;
       for (int n0 = 0; n0 < p.NT; n0 += 32) {
         uint32_t rr[32];
         tmem_ld32(t_lane + (uint32_t)(u * p.NT + n0), rr);
         tmem_ld_wait();
         if (valid) {
-#pragma unroll
-          for (int e = 0; e < 32; e += 4)
-            *reinterpret_cast<float4*>(p.ws + obase + n0 + e) =
-                make_float4(__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
+          const int ncols = min(32, p.cb_g - col0 - n0);
+          if (vec) {
+            for (int e = 0; e < ncols; e += 4)
+              *reinterpret_cast<float4*>(p.ws + obase + n0 + e) =
+                  make_float4(__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
+          } else {
+            for (int e = 0; e < ncols; ++e) p.ws[obase + n0 + e] = __uint_as_float(rr[e]);
+          }
         }
       }
     }
@@ -195,6 +209,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 }
 
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n, int nsplit) {
+  if (n & 3) {  // thin layers: split slices are not 16-byte aligned
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      float acc = ws[i];
+      for (int s = 1; s < nsplit; ++s) acc += ws[(long long)s * n + i];
+      dw[i] = acc;
+    }
+    return;
+  }
   const long long n4 = n / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     float4 acc = __ldg(reinterpret_cast<const float4*>(ws) + i);
@@ -219,13 +241,12 @@ struct WgPlan {
 static WgPlan make_plan(const KtConv1dDesc* d) {
   WgPlan pl{};
   pl.ok = false;
-  if (d->groups != 1) return pl;
   WgTcParams& p = pl.p;
   // gathered (A) side / base (B) side, see conv_ffma.cu: conv1d_bwd_weight_ffma
   const bool tr = d->transposed != 0;
   const int ca = tr ? d->c_out : d->c_in, cb = tr ? d->c_in : d->c_out;
-  if (ca % 64 != 0 || cb % 64 != 0) return pl;
-  if (ca != 64 && ca % 128 != 0) return pl;
+  p.groups = d->groups;
+  p.ca_g = ca / d->groups; p.cb_g = cb / d->groups;
   p.batch = d->batch; p.nsub = d->nsub; p.ca = ca; p.cb = cb; p.taps_total = d->kernel;
   p.t_a = tr ? d->t_out : d->t_in;
   p.t_b = tr ? d->t_in : d->t_out;
@@ -233,10 +254,11 @@ static WgPlan make_plan(const KtConv1dDesc* d) {
   p.step = d->stride;
   p.up = tr ? 1 : d->upsample;
   if (p.step > 8) return pl;
-  p.mode = ca == 64 ? 1 : 0;
-  p.NT = cb % 256 == 0 ? 256 : (cb % 128 == 0 ? 128 : 64);
-  p.n_cb_tiles = cb / p.NT;
-  p.n_ca_tiles = p.mode == 0 ? ca / 128 : 1;
+  // channels are zero-padded to 64-wide images: thin / grouped layers use the same kernel
+  p.mode = p.ca_g <= 64 ? 1 : 0;
+  p.NT = std::min(256, (p.cb_g + 63) & ~63);
+  p.n_cb_tiles = ceil_div(p.cb_g, p.NT);
+  p.n_ca_tiles = p.mode == 0 ? ceil_div(p.ca_g, 128) : 1;
   p.a_groups = p.mode == 0 ? 2 : 1;
   p.b_groups = p.NT / 64;
   const int U = std::min(kWgMaxUnits, 512 / p.NT);
@@ -286,11 +308,11 @@ static WgPlan make_plan(const KtConv1dDesc* d) {
   if (p.tmem_cols > 512) return pl;
   p.chunks_per_batch = ceil_div(p.M * p.nsub, kWgTK);
   const long long units = (long long)p.batch * p.chunks_per_batch;
-  const long long base = (long long)p.n_ca_tiles * p.n_cb_tiles * p.ngroups;
+  const long long base = (long long)p.groups * p.n_ca_tiles * p.n_cb_tiles * p.ngroups;
   long long nsplit = std::max<long long>(1, (148 + base - 1) / base);
   nsplit = std::min(nsplit, units);
   p.nsplit = (int)nsplit;
-  pl.ws_floats = nsplit * (long long)p.taps_total * ca * cb;
+  pl.ws_floats = nsplit * (long long)p.taps_total * p.ca_g * cb;
   pl.ok = true;
   return pl;
 }
@@ -323,11 +345,11 @@ int conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy,
     KT_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     cfg.store(true, std::memory_order_release);
   }
-  dim3 grid(p.n_ca_tiles * p.n_cb_tiles, p.ngroups, p.nsplit);
+  dim3 grid(p.groups * p.n_ca_tiles * p.n_cb_tiles, p.ngroups, p.nsplit);
   wgrad_tc_kernel<<<grid, kWgThreads, pl.smem, st>>>(p);
   KT_CHECK_CUDA(cudaGetLastError());
-  const long long n = (long long)p.taps_total * p.ca * p.cb;
-  const int blocks = (int)std::min<long long>((n / 4 + 255) / 256, 148LL * 8);
+  const long long n = (long long)p.taps_total * p.ca_g * p.cb;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, 148LL * 8));
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dw, n, p.nsplit);
   KT_CHECK_CUDA(cudaGetLastError());
   if (dbias) {

@@ -162,17 +162,17 @@ class PreparedWeight:
         self.key = None
         self.img = {}          # (dir, n_tile) -> packed split-bf16 tcgen05 weight tiles
 
-    def tc_image(self, spec, direction, n_tile):
-        """hi/lo bf16 SWIZZLE_128B weight tiles for the tcgen05 kernels (kt_weight_pack_tc)."""
+    def tc_image(self, spec, d, direction, n_tile):
+        """hi/lo bf16 SWIZZLE_128B weight tiles for the tcgen05 kernels (kt_weight_pack_tc).  The tiling
+        (N tile, padding) can depend on the sequence length, hence the key on n_tile."""
         k = (direction, n_tile)
         img = self.img.get(k)
         if img is None:
-            cin_g = spec.c_in // spec.groups
-            # contraction dim K / produced dim N of this direction's GEMM
-            kdim, ndim = (cin_g, spec.c_out) if direction == 0 else (spec.c_out // spec.groups, spec.c_in)
+            lib = _lib.load()
             src = self.w_fwd if direction == 0 else self.w_bwd
-            img = torch.empty(spec.kernel * kdim * ndim * 2, device=src.device, dtype=torch.bfloat16)
-            check(_lib.load().kt_weight_pack_tc(ptr(src), spec.kernel, kdim, ndim, n_tile, ptr(img), stream_ptr()),
+            nbytes = int(lib.kt_conv1d_tc_image_bytes(ctypes.byref(d), direction))
+            img = torch.empty(nbytes // 2, device=src.device, dtype=torch.bfloat16)
+            check(lib.kt_weight_pack_tc(ctypes.byref(d), direction, ptr(src), ptr(img), stream_ptr()),
                   "kt_weight_pack_tc")
             _count()
             self.img[k] = img
@@ -274,7 +274,7 @@ class ConvFn(torch.autograd.Function):
         flops, nbytes = _conv_work(spec, d)
         if nt:
             global _tc_launches
-            img = pw.tc_image(spec, 0, nt)
+            img = pw.tc_image(spec, d, 0, nt)
             with _timed("conv_fwd_tc", flops, nbytes, _sig(spec, d)):
                 check(lib.kt_conv1d_fwd_tc(ctypes.byref(d), ptr(x), ptr(img), ptr(bd), ptr(resid),
                                            ptr(y), stream_ptr()), "kt_conv1d_fwd_tc")
@@ -288,7 +288,7 @@ class ConvFn(torch.autograd.Function):
         ctx.w_bwd, ctx.norm = pw.w_bwd, pw.norm
         nt_b = _tc_tile(lib, spec, d, 1) if x.requires_grad else 0
         ctx.nt_bwd = nt_b
-        ctx.img_bwd = pw.tc_image(spec, 1, nt_b) if nt_b else None
+        ctx.img_bwd = pw.tc_image(spec, d, 1, nt_b) if nt_b else None
         ctx.has_resid, ctx.has_bias, ctx.has_g = resid is not None, bias is not None, g is not None
         ctx.save_for_backward(x, y if spec.act_out != KT_ACT_NONE else None, v, g)
         return y

@@ -201,8 +201,8 @@ class GanStep:
         with torch.cuda.graph(g3, pool=g1.pool()):
             self._seg_dopt()
         self._graphs = (g1, g2, g3)
-        self.steps += 1        # the capture pass executed one real step
-        return dict(self._log)
+        # stream capture only RECORDS the kernels: run the step for real by replaying what was captured
+        return self._replay(y, x)
 
     def _replay(self, y, x):
         sy, sx = self._static
