@@ -155,27 +155,30 @@ class PreparedWeight:
     """Kernel-layout copies of one layer's effective weight (w_fwd, w_bwd) + the weight-norm
     row norms, valid for one (parameter version) -- see kt_weight_prepare."""
 
-    __slots__ = ("w_fwd", "w_bwd", "norm", "key", "img")
+    __slots__ = ("w_fwd", "w_bwd", "norm", "key", "img", "img_stale")
 
     def __init__(self):
         self.w_fwd = self.w_bwd = self.norm = None
         self.key = None
         self.img = {}          # (dir, n_tile) -> packed split-bf16 tcgen05 weight tiles
+        self.img_stale = set()
 
     def tc_image(self, spec, d, direction, n_tile):
         """hi/lo bf16 SWIZZLE_128B weight tiles for the tcgen05 kernels (kt_weight_pack_tc).  The tiling
         (N tile, padding) can depend on the sequence length, hence the key on n_tile."""
         k = (direction, n_tile)
         img = self.img.get(k)
-        if img is None:
+        if img is None or k in self.img_stale:
             lib = _lib.load()
             src = self.w_fwd if direction == 0 else self.w_bwd
-            nbytes = int(lib.kt_conv1d_tc_image_bytes(ctypes.byref(d), direction))
-            img = torch.empty(nbytes // 2, device=src.device, dtype=torch.bfloat16)
+            if img is None:
+                nbytes = int(lib.kt_conv1d_tc_image_bytes(ctypes.byref(d), direction))
+                img = torch.empty(nbytes // 2, device=src.device, dtype=torch.bfloat16)
+                self.img[k] = img
             check(lib.kt_weight_pack_tc(ctypes.byref(d), direction, ptr(src), ptr(img), stream_ptr()),
                   "kt_weight_pack_tc")
             _count()
-            self.img[k] = img
+            self.img_stale.discard(k)
         return img
 
 
@@ -196,17 +199,23 @@ def prepare_weight(cache, spec, v, g):
     vd = v.detach()
     if not vd.is_contiguous():
         vd = vd.contiguous()
-    cache.w_fwd = torch.empty(spec.w_numel, device=v.device, dtype=torch.float32)
-    cache.w_bwd = torch.empty(spec.w_numel, device=v.device, dtype=torch.float32)
+    # The buffers are allocated ONCE and rewritten in place: under CUDA-graph replay the forward of the next
+    # step must read the very memory the captured prepare / pack kernels of this step wrote.
     mode = 0 if g is None else 1
-    cache.norm = torch.empty(d0, device=v.device, dtype=torch.float32) if mode else None
+    # (A recomputed spectral-norm weight differs between two forwards of the same step whose backward is
+    # still pending, so it always gets fresh buffers.)
+    if key is None or cache.w_fwd is None or cache.w_fwd.device != v.device or cache.w_fwd.numel() != spec.w_numel:
+        cache.w_fwd = torch.empty(spec.w_numel, device=v.device, dtype=torch.float32)
+        cache.w_bwd = torch.empty(spec.w_numel, device=v.device, dtype=torch.float32)
+        cache.norm = torch.empty(d0, device=v.device, dtype=torch.float32) if mode else None
+        cache.img = {}
     gd = None if g is None else g.detach().contiguous()
     check(lib.kt_weight_prepare(ptr(vd), ptr(gd), None, mode, d0, d1, k, int(spec.transposed), spec.groups,
                                 ptr(cache.w_fwd), ptr(cache.w_bwd), ptr(cache.norm), None, stream_ptr()),
           "kt_weight_prepare")
     _count()
     cache.key = key
-    cache.img = {}
+    cache.img_stale = set(cache.img)      # packed tcgen05 tiles are re-packed (in place) on next use
     return cache
 
 
