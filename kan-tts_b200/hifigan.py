@@ -13,6 +13,7 @@ Out of scope: NSF source module, MultiSpecDiscriminator, 
 """
 import copy
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -24,6 +25,19 @@ from ._lib import KT_ACT_LRELU, KT_ACT_NONE, KT_ACT_TANH, KT_PATH_AUTO
 # --------------------------------------------------------------------------------------------
 # parameter holders (names / shapes == the reference's weight_norm / spectral_norm wrapped convs)
 # --------------------------------------------------------------------------------------------
+
+
+_PARALLEL_STREAMS = os.environ.get("KANTTS_B200_STREAMS", "1") != "0"
+_STREAMS = {}
+
+
+def _side_streams(device, n):
+    """Per-device pool of side streams for the independent sub-discriminators."""
+    key = (device.type, device.index)
+    pool = _STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]
 
 
 def _consume_init_weights_rng(weight):
@@ -282,7 +296,19 @@ class Generator(nn.Module):
             x = ops.SinAddFn.apply(x)                                        # hifigan.py:157
             rep = self.repeat_upsamples[i][2].forward_rows(x)                # :158
             x = self.transpose_upsamples[i][1].forward_rows(x, resid=rep)    # :160,168 (crop fused: t_out)
-            rs = [self.conv_blocks[i * self.num_kernels + j].forward_rows(x) for j in range(self.num_kernels)]
+            par = x.is_cuda and _PARALLEL_STREAMS and self.num_kernels > 1
+            if par:                                                           # the parallel resblocks are independent
+                cur = torch.cuda.current_stream()
+                streams = _side_streams(x.device, self.num_kernels)
+                rs = []
+                for j in range(self.num_kernels):
+                    streams[j].wait_stream(cur)
+                    with torch.cuda.stream(streams[j]):
+                        rs.append(self.conv_blocks[i * self.num_kernels + j].forward_rows(x))
+                for s in streams[: self.num_kernels]:
+                    cur.wait_stream(s)
+            else:
+                rs = [self.conv_blocks[i * self.num_kernels + j].forward_rows(x) for j in range(self.num_kernels)]
             rs += [None] * (3 - len(rs))
             x = ops.Mean3Fn.apply(1.0 / self.num_kernels, *rs)               # :170-176
         return self.conv_post.forward_rows(x)                                # :178-180
@@ -376,11 +402,26 @@ class MultiPeriodDiscriminator(nn.Module):
             self.discriminators += [PeriodDiscriminator(**params)]
 
     def forward(self, y):
+        # The period discriminators are independent and their late layers are too small to fill 148 SMs:
+        # run them on side streams (fork / join around the loop; autograd replays the same streams in
+        # backward, and CUDA-graph capture records the branches as parallel graph paths).
         y_d_rs, fmap_rs = [], []
-        for d in self.discriminators:
-            y_d_r, fmap_r = d(y)
+        par = y.is_cuda and _PARALLEL_STREAMS and len(self.discriminators) > 1
+        if par:
+            cur = torch.cuda.current_stream()
+            streams = _side_streams(y.device, len(self.discriminators))
+        for i, d in enumerate(self.discriminators):
+            if par:
+                streams[i].wait_stream(cur)
+                with torch.cuda.stream(streams[i]):
+                    y_d_r, fmap_r = d(y)
+            else:
+                y_d_r, fmap_r = d(y)
             y_d_rs.append(y_d_r)
             fmap_rs.append(fmap_r)
+        if par:
+            for s in streams:
+                cur.wait_stream(s)
         return y_d_rs, fmap_rs
 
 
@@ -499,11 +540,25 @@ class MultiScaleDiscriminator(nn.Module):
         """y: (B, 1, T) -> (list of (B, n_i), list of list of (B, C, T_l) feature maps)"""
         y_d_rs, fmap_rs = [], []
         rows = y.transpose(1, 2).contiguous()                                 # (B, T, 1)
+        inputs = [rows]
+        for i in range(1, len(self.discriminators)):                          # the pooling chain is cheap and serial
+            cat = ops.DwtFn.apply(rows.reshape(rows.shape[0], -1))            # (B, T2, 2) = cat([yl, yh], 1)
+            rows = self.aux_convs[i - 1].run(cat)                              # (B, T2, 1), lrelu fused
+            inputs.append(rows)
+        par = y.is_cuda and _PARALLEL_STREAMS and len(self.discriminators) > 1
+        if par:                                                               # the scales themselves are independent
+            cur = torch.cuda.current_stream()
+            streams = _side_streams(y.device, len(self.discriminators))
         for i, d in enumerate(self.discriminators):
-            if i != 0:
-                cat = ops.DwtFn.apply(rows.reshape(rows.shape[0], -1))        # (B, T2, 2) = cat([yl, yh], 1)
-                rows = self.aux_convs[i - 1].run(cat)                          # (B, T2, 1), lrelu fused
-            y_d_r, fmap_r = d.forward_rows(rows)
+            if par:
+                streams[i].wait_stream(cur)
+                with torch.cuda.stream(streams[i]):
+                    y_d_r, fmap_r = d.forward_rows(inputs[i])
+            else:
+                y_d_r, fmap_r = d.forward_rows(inputs[i])
             y_d_rs.append(y_d_r)
             fmap_rs.append(fmap_r)
+        if par:
+            for s in streams:
+                cur.wait_stream(s)
         return y_d_rs, fmap_rs
