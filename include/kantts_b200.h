@@ -159,8 +159,13 @@ int kt_dwt_db3_bwd(const float* dy, float* dx, int32_t batch, int32_t t, void* s
  * n_fft must be a power of two in [64, 4096] (all shipped configs: 512 / 1024 / 2048). */
 typedef struct KtMelDesc {
   int32_t batch, t, n_fft, hop, n_mels, frames; /* frames = t / hop + 1 (center=True) */
-  int32_t pad_mode;                              /* 0 zeros (MelSpectrogram), 1 reflect (stft()) */
-  float eps;                                     /* 1e-10 (mel) / 1e-7 (stft loss) */
+  int32_t pad_mode;                              /* 0 zeros (MelSpectrogram), 1 reflect (stft(), librosa.stft) */
+  float eps;                                     /* amplitude clamp: 1e-10 (mel) / 1e-7 (stft loss) / 0 (dsp.py) */
+  /* dB normalisation: v = clamp(norm_scale * ((20*log10(max(mel, 1e-5)) - ref_db - min_db) / -min_db) - norm_shift,
+   * norm_lo, norm_hi).  MelSpectrogram (audio_torch.py:42-63): ref 20, min -100, scale 8, shift 4, [-4, 4];
+   * offline dsp.melspectrogram (preprocess/audio_processor/core/dsp.py:66-74,165-201): scale max_norm, shift 0,
+   * [0, max_norm]  (symmetric=True: scale 2*max_norm, shift max_norm, [-max_norm, max_norm]). */
+  float ref_db, min_db, norm_scale, norm_shift, norm_lo, norm_hi;
 } KtMelDesc;
 /* Outputs (each optional / NULL): mel [B][n_mels][frames] (needs melmat), amp [B][frames][n_bins]
  * (the clamped magnitude, audio_torch.py:31), spec [B][frames][n_bins][2] (re, im; saved for bwd). */

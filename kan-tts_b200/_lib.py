@@ -31,7 +31,7 @@ class KtConv1dDesc(ctypes.Structure):
 
 class KtMelDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("batch", "t", "n_fft", "hop", "n_mels", "frames", "pad_mode")] + \
-               [("eps", ctypes.c_float)]
+               [(n, ctypes.c_float) for n in ("eps", "ref_db", "min_db", "norm_scale", "norm_shift", "norm_lo", "norm_hi")]
 
 
 _P = ctypes.c_void_p

@@ -90,3 +90,25 @@ def stft(x, fft_size, hop_size, win_length, window):
         left = (fft_size - w.numel()) // 2
         w = torch.nn.functional.pad(w, (left, fft_size - w.numel() - left))
     return ops.StftMelFn.apply(x, w.contiguous(), None, fft_size, hop_size, 1, 1e-7)
+
+
+def melspectrogram(y, sample_rate, n_fft=1024, hop_length=256, win_length=1024, n_mels=80, max_norm=1.0,
+                   min_level_db=-100, ref_level_db=20, fmin=50, fmax=8000, symmetric=False, preemphasize=False,
+                   device="cuda"):
+    """The OFFLINE feature-extraction mel of kantts/preprocess/audio_processor/core/dsp.py:165-201 on the fused
+    STFT kernel: librosa.stft framing (centre, reflect padding, periodic hann), |D| (no clamp), Slaney mel
+    projection, 20*log10(max(1e-5, .)) - ref_level_db, dsp._normalize ([0, max_norm], or symmetric).
+    y: 1-D waveform (numpy / tensor) -> numpy array (frames, n_mels) like the reference."""
+    assert fmax <= sample_rate // 2
+    yt = torch.as_tensor(np.asarray(y) if not torch.is_tensor(y) else y, dtype=torch.float32).reshape(1, -1)
+    if preemphasize:                                              # dsp.py:53-56: lfilter([1, -0.98], [1], wav)
+        yt = torch.cat([yt[:, :1], yt[:, 1:] - 0.98 * yt[:, :-1]], dim=1)
+    yt = yt.to(device)
+    melmat = torch.from_numpy(slaney_mel_filterbank(sample_rate, n_fft, n_mels, fmin, fmax).T.copy()).to(device)
+    if symmetric:
+        norm = (float(ref_level_db), float(min_level_db), 2.0 * max_norm, float(max_norm), -float(max_norm), float(max_norm))
+    else:
+        norm = (float(ref_level_db), float(min_level_db), float(max_norm), 0.0, 0.0, float(max_norm))
+    mel = ops.StftMelFn.apply(yt, _padded_window(win_length, n_fft, yt.device), melmat.contiguous(), n_fft, hop_length,
+                              1, 0.0, norm)
+    return mel[0].transpose(0, 1).contiguous().cpu().numpy()

@@ -38,7 +38,7 @@ __device__ void fft_inplace(float2* s, int n, int logn, float sign) {
 
 struct MelParams {
   int batch, t, n_fft, hop, n_mels, frames, logn, pad_mode;
-  float eps;
+  float eps, ref_db, min_db, norm_scale, norm_shift, norm_lo, norm_hi;
 };
 
 __device__ __forceinline__ int src_index(int pos, int t, int pad_mode) {
@@ -82,10 +82,10 @@ __global__ void __launch_bounds__(256) stft_mel_fwd_kernel(MelParams p, const fl
       float acc = 0.f;
       for (int k = 0; k < nb; ++k) acc = fmaf(amp[k], __ldg(melmat + (long long)k * p.n_mels + m), acc);
       acc = fmaxf(acc, p.eps);
-      const float db = 20.f * log10f(fmaxf(acc, 1e-5f)) - 20.f;
-      // spectral_normalize_torch (audio_torch.py:42-63): 2*4*((db+100)/100) - 4, clamped to [-4, 4]
-      float v = 8.f * ((db + 100.f) / 100.f) - 4.f;
-      v = fminf(fmaxf(v, -4.f), 4.f);
+      const float db = 20.f * log10f(fmaxf(acc, 1e-5f)) - p.ref_db;
+      // spectral_normalize_torch (audio_torch.py:42-63) / dsp._normalize (dsp.py:66-74)
+      float v = p.norm_scale * ((db - p.min_db) / (-p.min_db)) - p.norm_shift;
+      v = fminf(fmaxf(v, p.norm_lo), p.norm_hi);
       mel[((long long)b * p.n_mels + m) * p.frames + f] = v;
     }
   }
@@ -117,10 +117,10 @@ __global__ void __launch_bounds__(256) stft_mel_bwd_kernel(MelParams p, const fl
       float gr = __ldg(dmel + ((long long)b * p.n_mels + m) * p.frames + f);
       const float melc = fmaxf(acc, p.eps);
       const float x = fmaxf(melc, 1e-5f);
-      const float db = 20.f * log10f(x) - 20.f;
-      const float v = 8.f * ((db + 100.f) / 100.f) - 4.f;
-      if (!(v >= -4.f && v <= 4.f) || melc < 1e-5f || acc < p.eps) gr = 0.f;
-      dm[m] = gr * (0.08f * 20.f * 0.4342944819032518f) / x;  // d/dx [0.08*(20 log10 x)] = 1.6 / (x ln 10)
+      const float db = 20.f * log10f(x) - p.ref_db;
+      const float v = p.norm_scale * ((db - p.min_db) / (-p.min_db)) - p.norm_shift;
+      if (!(v >= p.norm_lo && v <= p.norm_hi) || melc < 1e-5f || acc < p.eps) gr = 0.f;
+      dm[m] = gr * (p.norm_scale / (-p.min_db) * 20.f * 0.4342944819032518f) / x;  // d/dx [scale/(-min) * 20 log10 x]
     }
   }
   __syncthreads();
@@ -161,6 +161,9 @@ static int fill(MelParams& p, const KtMelDesc* d) {
   KT_REQUIRE(d->n_mels >= 0 && d->n_mels <= 256, "stft_mel: n_mels=%d unsupported", d->n_mels);
   p.batch = d->batch; p.t = d->t; p.n_fft = d->n_fft; p.hop = d->hop; p.n_mels = d->n_mels; p.frames = d->frames;
   p.logn = logn; p.pad_mode = d->pad_mode; p.eps = d->eps;
+  p.ref_db = d->ref_db; p.min_db = d->min_db; p.norm_scale = d->norm_scale; p.norm_shift = d->norm_shift;
+  p.norm_lo = d->norm_lo; p.norm_hi = d->norm_hi;
+  KT_REQUIRE(d->n_mels == 0 || d->min_db < 0.f, "stft_mel: min_db must be negative");
   return KT_OK;
 }
 

@@ -437,13 +437,15 @@ class StftMelFn(torch.autograd.Function):
     when ``melmat`` is given, else the magnitude (B, frames, n_bins)."""
 
     @staticmethod
-    def forward(ctx, wav, window, melmat, n_fft, hop, pad_mode, eps):
+    def forward(ctx, wav, window, melmat, n_fft, hop, pad_mode, eps, norm=(20.0, -100.0, 8.0, 4.0, -4.0, 4.0)):
         wav = wav.contiguous()
         B, T = wav.shape
         frames = T // hop + 1
         nb = n_fft // 2 + 1
         n_mels = 0 if melmat is None else melmat.shape[1]
-        d = KtMelDesc(batch=B, t=T, n_fft=n_fft, hop=hop, n_mels=n_mels, frames=frames, pad_mode=pad_mode, eps=eps)
+        d = KtMelDesc(batch=B, t=T, n_fft=n_fft, hop=hop, n_mels=n_mels, frames=frames, pad_mode=pad_mode, eps=eps,
+                      ref_db=norm[0], min_db=norm[1], norm_scale=norm[2], norm_shift=norm[3], norm_lo=norm[4],
+                      norm_hi=norm[5])
         spec = torch.empty(B, frames, nb, 2, device=wav.device, dtype=torch.float32) \
             if ctx.needs_input_grad[0] else None
         mel = amp = None
@@ -469,7 +471,7 @@ class StftMelFn(torch.autograd.Function):
         check(_lib.load().kt_stft_mel_bwd(ctypes.byref(d), ptr(dmel), ptr(damp), ptr(spec), ptr(window), ptr(melmat),
                                          ptr(dwav), stream_ptr()), "kt_stft_mel_bwd")
         _count(2)
-        return dwav, None, None, None, None, None, None
+        return dwav, None, None, None, None, None, None, None
 
 
 def l1_sum(a, b, scale=1.0):

@@ -117,7 +117,6 @@ class GanStep:
         log["generator_loss"] = gen_loss
         self.g_grads.zero()
         gen_loss.backward()
-        self._detach_log()
 
     def _seg_gopt_discriminator(self, y, x):
         """generator Adam (trainer.py:547-553), then discriminator forward/backward (:556-580)"""
@@ -142,14 +141,6 @@ class GanStep:
             for fg in self.d_grads.values():
                 fg.zero()
             dis_loss.backward()
-            self._detach_log()
-
-    def _detach_log(self):
-        """Logged losses must not keep the autograd graph (and its AccumulateGrad nodes) alive across steps:
-        a stale node bound to another stream would force a cross-stream sync inside CUDA-graph capture."""
-        for k, v in self._log.items():
-            if torch.is_tensor(v):
-                self._log[k] = v.detach()
 
     def _seg_dopt(self):
         """discriminator Adam (trainer.py:581-589)"""
@@ -174,7 +165,11 @@ class GanStep:
                 fg.all_reduce_mean()
         self._seg_dopt()
         self.steps += 1
-        return dict(self._log)
+        # hand out detached losses and drop our own references: a caller holding last step's losses must not
+        # keep the autograd graph (and its stream-bound AccumulateGrad nodes) alive into a later graph capture
+        out = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in self._log.items()}
+        self._log = {}
+        return out
 
     def invalidate_weight_caches(self):
         """Forget every prepared (kernel-layout) weight: needed when eager launches follow graph replays,

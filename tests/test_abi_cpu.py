@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_descriptor_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.KtConv1dDesc) == 18 * 4
-    assert ctypes.sizeof(_lib.KtMelDesc) == 8 * 4
+    assert ctypes.sizeof(_lib.KtMelDesc) == 14 * 4
 
 
 def test_state_dict_contract_matches_golden(golden):
