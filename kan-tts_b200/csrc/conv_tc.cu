@@ -85,9 +85,15 @@ struct TcParams {
   int kg;        // contraction channels per tile (C_in, or C_in / groups)
   int grouped;   // 1: N tile nt = group nt (input channels [nt * kg, +kg), outputs [nt * n_stride, +n_stride))
   int n_stride;  // output channels advanced per N tile
-  // phase: out[(o_off + o_step*m), w] = sum_n W[tap_j[n]] in[(m + q_n)*i_step + rho_n, w]
-  int M, o_off, o_step, i_step, up, accumulate;
-  int ngroups;                        // residue classes actually used
+  // phases: out[(o_off + o_step*m), w] = sum_n W[tap_j[n]] in[(m + q_n)*i_step + rho_n, w].  All polyphase
+  // phases of a layer (the `stride` output residues of a transposed conv / strided data gradient) run in ONE
+  // launch: the m-tile index space is the concatenation of the phases' tiles.
+  int nphases;
+  int ph_M[kTcMaxGroups], ph_ooff[kTcMaxGroups];
+  int ph_mt0[kTcMaxGroups + 1];       // first m-tile of each phase
+  int ph_g0[kTcMaxGroups + 1];        // first residue group of each phase
+  int o_step, i_step, up, accumulate;
+  int ngroups;                        // residue groups over all phases
   int grp_rho[kTcMaxGroups];
   int grp_qlo[kTcMaxGroups];
   int grp_first[kTcMaxGroups + 1];    // taps of group g: [grp_first[g], grp_first[g+1])
@@ -120,8 +126,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int F = p.M * p.nsub;         // flattened outputs (m * nsub + w) per batch item in this phase
-  const int mtiles = (F + kTcM - 1) / kTcM;
+  const int mtiles = p.ph_mt0[p.nphases];   // m-tiles of all phases (each: 128 flattened outputs m * nsub + w)
   const int total_tiles = mtiles * p.ntiles * p.batch;
 
   if (tid == 0) {
@@ -142,11 +147,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     // ===================== activation producers =====================
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int mt = tile % mtiles, bb = tile / (mtiles * p.ntiles);
+      const int gm = tile % mtiles, bb = tile / (mtiles * p.ntiles);
+      int ph = 0;
+      while (gm >= p.ph_mt0[ph + 1]) ++ph;
       const int ch_base = p.grouped ? ((tile / mtiles) % p.ntiles) * p.kg : 0;
-      const int f0 = mt * kTcM;
+      const int f0 = (gm - p.ph_mt0[ph]) * kTcM;
       for (int c = 0; c < p.kchunks; ++c) {
-        for (int g = 0; g < p.ngroups; ++g, ++it) {
+        for (int g = p.ph_g0[ph]; g < p.ph_g0[ph + 1]; ++g, ++it) {
           const int s = it % p.na_stages;
           mbar_wait(&empty_a[s], ((it / p.na_stages) & 1) ^ 1);
           uint8_t* img_hi = a_base + (size_t)s * a_stage_bytes;
@@ -167,8 +174,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = (tile / mtiles) % p.ntiles;
+        int ph = 0;
+        while ((tile % mtiles) >= p.ph_mt0[ph + 1]) ++ph;
+        const int n_begin = p.grp_first[p.ph_g0[ph]], n_end = p.grp_first[p.ph_g0[ph + 1]];
         for (int c = 0; c < p.kchunks; ++c) {
-          for (int n = 0; n < p.ntaps; ++n, ++it) {  // taps are ordered by group: same order as the MMA issuer
+          for (int n = n_begin; n < n_end; ++n, ++it) {  // taps are ordered by group: same order as the MMA issuer
             const int s = it % p.nb_stages;
             mbar_wait(&empty_b[s], ((it / p.nb_stages) & 1) ^ 1);
             const long long block = ((long long)p.tap_j[n] * p.kchunks + c) * p.ntiles + nt;
@@ -191,9 +201,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         tc_fence_after();
         const uint32_t d_tmem = tmem_acc + (uint32_t)buf * buf_cols;
         uint32_t acc = 0;
+        int ph = 0;
+        while ((tile % mtiles) >= p.ph_mt0[ph + 1]) ++ph;
         for (int c = 0; c < p.kchunks; ++c) {
           const int kslices = (min(kTcKC, p.kg - c * kTcKC) + 15) >> 4;   // K = 16 slices holding real channels
-          for (int g = 0; g < p.ngroups; ++g, ++it_a) {
+          for (int g = p.ph_g0[ph]; g < p.ph_g0[ph + 1]; ++g, ++it_a) {
             const int sa = it_a % p.na_stages;
             mbar_wait(&full_a[sa], (it_a / p.na_stages) & 1);
             tc_fence_after();
@@ -231,7 +243,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     const int quarter = warp & 3;
     int ti = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-      const int mt = tile % mtiles, nt = (tile / mtiles) % p.ntiles, bb = tile / (mtiles * p.ntiles);
+      const int gm = tile % mtiles, nt = (tile / mtiles) % p.ntiles, bb = tile / (mtiles * p.ntiles);
+      int ph = 0;
+      while (gm >= p.ph_mt0[ph + 1]) ++ph;
+      const int mt = gm - p.ph_mt0[ph];
+      const int F = p.ph_M[ph] * p.nsub;
       const int buf = ti & 1;
       mbar_wait(&tmem_full[buf], (ti >> 1) & 1);
       tc_fence_after();
@@ -239,7 +255,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       const bool valid = f < F;
       const int m = valid ? (p.nsub == 1 ? f : f / p.nsub) : 0;
       const int w = valid ? f - m * p.nsub : 0;
-      const int to = p.o_off + p.o_step * m;
+      const int to = p.ph_ooff[ph] + p.o_step * m;
       const long long obase = (((long long)bb * p.t_out + to) * p.nsub + w) * p.c_out + (long long)nt * p.n_stride;
       const int n_valid = min(p.n_stride, p.c_out - nt * p.n_stride);   // real output channels of this tile
       const bool vec_out = ((n_valid | p.c_out | p.n_stride) & 3) == 0;
@@ -364,11 +380,19 @@ static TcLayerPlan layer_plan(const KtConv1dDesc* d, int dir) {
 
 std::vector<Phase> conv_phases(const KtConv1dDesc* d, int dir);  // conv_ffma.cu
 
-// Phase -> residue groups.  Returns false when the phase does not fit the kernel's limits.
-static bool fill_groups(TcParams& p, const Phase& ph, int nsub) {
-  p.M = ph.M; p.o_off = ph.o_off; p.o_step = ph.o_step; p.i_step = ph.i_step; p.up = ph.up; p.accumulate = ph.accumulate;
+// Append one phase (its residue groups and taps) to the launch parameters.  Returns false when the
+// phase does not fit the kernel's limits.  Call reset_phases() first.
+static void reset_phases(TcParams& p) {
+  p.nphases = 0; p.ngroups = 0; p.ntaps = 0; p.rows = 0;
+  p.ph_mt0[0] = 0; p.ph_g0[0] = 0; p.grp_first[0] = 0;
+}
+
+static bool add_phase(TcParams& p, const Phase& ph, int nsub) {
+  if (ph.M <= 0) return true;
   const int s = ph.i_step;
-  if (s < 1 || s > kTcMaxGroups) return false;
+  if (s < 1 || s > kTcMaxGroups || p.nphases >= kTcMaxGroups) return false;
+  if (p.nphases > 0 && (p.o_step != ph.o_step || p.i_step != ph.i_step || p.up != ph.up)) return false;
+  p.o_step = ph.o_step; p.i_step = ph.i_step; p.up = ph.up; p.accumulate = ph.accumulate;
   int q[kMaxTaps], rho[kMaxTaps];
   for (int n = 0; n < ph.ntaps; ++n) {
     if (ph.tap_ioff[n] < -(1 << 24)) {  // placeholder tap of an output residue no real tap reaches
@@ -378,14 +402,13 @@ static bool fill_groups(TcParams& p, const Phase& ph, int nsub) {
     q[n] = fdiv(ph.tap_ioff[n], s);
     rho[n] = ph.tap_ioff[n] - q[n] * s;
   }
-  p.ngroups = 0;
-  p.ntaps = 0;
   int max_span = 0;
   for (int r = 0; r < s; ++r) {
     int qlo = 1 << 30, qhi = -(1 << 30), cnt = 0;
     for (int n = 0; n < ph.ntaps; ++n)
       if (rho[n] == r) { qlo = std::min(qlo, q[n]); qhi = std::max(qhi, q[n]); ++cnt; }
     if (!cnt) continue;
+    if (p.ngroups >= kTcMaxGroups || p.ntaps + cnt > kMaxTaps) return false;
     const int g = p.ngroups++;
     p.grp_rho[g] = r; p.grp_qlo[g] = qlo; p.grp_first[g] = p.ntaps;
     for (int n = 0; n < ph.ntaps; ++n)
@@ -394,15 +417,34 @@ static bool fill_groups(TcParams& p, const Phase& ph, int nsub) {
         p.tap_shift[p.ntaps] = (q[n] - qlo) * nsub;
         ++p.ntaps;
       }
+    p.grp_first[p.ngroups] = p.ntaps;
     max_span = std::max(max_span, (qhi - qlo) * nsub);
   }
-  p.grp_first[p.ngroups] = p.ntaps;
-  if (max_span > (1 << 20)) {  // a phase that no tap reaches (dummy tap far outside): keep one empty image
-    max_span = 0;
-    for (int n = 0; n < p.ntaps; ++n) p.tap_shift[n] = 0;
-  }
-  p.rows = (kTcM + max_span + 7) & ~7;
+  const int i = p.nphases++;
+  p.ph_M[i] = ph.M; p.ph_ooff[i] = ph.o_off;
+  p.ph_mt0[i + 1] = p.ph_mt0[i] + ceil_div(ph.M * nsub, kTcM);
+  p.ph_g0[i + 1] = p.ngroups;
+  p.rows = std::max(p.rows, (kTcM + max_span + 7) & ~7);
   return p.rows <= kTcMaxRows;
+}
+
+// Split the phases of a layer into launches: phases that fit together (and do not accumulate) share one.
+static bool plan_launches(const std::vector<Phase>& phases, int nsub, std::vector<TcParams>& out, const TcParams& base) {
+  TcParams cur = base;
+  reset_phases(cur);
+  for (const Phase& ph : phases) {
+    TcParams trial = cur;
+    if (ph.accumulate || cur.accumulate || !add_phase(trial, ph, nsub)) {
+      if (cur.nphases > 0) out.push_back(cur);
+      cur = base;
+      reset_phases(cur);
+      if (!add_phase(cur, ph, nsub)) return false;
+    } else {
+      cur = trial;
+    }
+  }
+  if (cur.nphases > 0) out.push_back(cur);
+  return true;
 }
 
 // Is (direction dir: 0 fwd, 1 bwd_data) of this layer runnable on the tcgen05 kernel?  -> N tile or 0
@@ -410,9 +452,8 @@ int tc_plan(const KtConv1dDesc* d, int dir) {
   if (dir == 1 && d->upsample > 1) return 0;          // `upsample` single-tap residue phases: staging-bound, stays FFMA
   const TcLayerPlan L = layer_plan(d, dir);
   if (!L.ok) return 0;
-  TcParams p{};
-  for (const Phase& ph : conv_phases(d, dir))
-    if (!fill_groups(p, ph, d->nsub)) return 0;
+  std::vector<TcParams> launches;
+  if (!plan_launches(conv_phases(d, dir), d->nsub, launches, TcParams{})) return 0;
   return L.NT;
 }
 
@@ -444,9 +485,7 @@ static int sm_count() {
   return n;
 }
 
-static int run_tc(TcParams p, const Phase& ph, cudaStream_t st) {
-  if (ph.M <= 0) return KT_OK;
-  KT_REQUIRE(fill_groups(p, ph, p.nsub), "conv_tc: phase exceeds kernel limits (input step %d)", ph.i_step);
+static int run_tc(TcParams p, cudaStream_t st) {   // p: phases already planned by plan_launches
   p.tmem_cols = 32;
   while (p.tmem_cols < p.NT) p.tmem_cols <<= 1;
   p.tmem_cols *= 2;                                   // two accumulator buffers
@@ -463,7 +502,7 @@ static int run_tc(TcParams p, const Phase& ph, cudaStream_t st) {
     KT_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     cfg.store(true, std::memory_order_release);
   }
-  const long long tiles = (long long)ceil_div(p.M * p.nsub, kTcM) * p.ntiles * p.batch;
+  const long long tiles = (long long)p.ph_mt0[p.nphases] * p.ntiles * p.batch;
   const int grid = (int)std::min<long long>(tiles, sm_count());
   conv_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
   KT_CHECK_CUDA(cudaGetLastError());
@@ -489,8 +528,10 @@ int conv1d_fwd_tc(const KtConv1dDesc* d, const float* x, const void* wimg, const
   p.bias = bias; p.resid = resid; p.mask = Side{nullptr, nullptr, 0, 0.f}; p.out = y;
   p.batch = d->batch; p.nsub = d->nsub; p.t_in = d->t_in; p.t_out = d->t_out; p.c_in = d->c_in; p.c_out = d->c_out;
   p.out_act = d->act_out; p.out_slope = d->act_out_slope;
-  for (const Phase& ph : conv_phases(d, 0)) {
-    int rc = run_tc(p, ph, st);
+  std::vector<TcParams> launches;
+  KT_REQUIRE(plan_launches(conv_phases(d, 0), d->nsub, launches, p), "conv1d_fwd_tc: phases exceed kernel limits");
+  for (const TcParams& lp : launches) {
+    int rc = run_tc(lp, st);
     if (rc) return rc;
   }
   return KT_OK;
@@ -511,8 +552,10 @@ int conv1d_bwd_data_tc(const KtConv1dDesc* d, const float* dy, const float* y, c
   // roles swap: the gathered tensor is dy (c_out channels, t_out rows), the product is dx
   p.batch = d->batch; p.nsub = d->nsub; p.t_in = d->t_out; p.t_out = d->t_in; p.c_in = d->c_out; p.c_out = d->c_in;
   p.out_act = KT_ACT_NONE; p.out_slope = 0.f;
-  for (const Phase& ph : conv_phases(d, 1)) {
-    int rc = run_tc(p, ph, st);
+  std::vector<TcParams> launches;
+  KT_REQUIRE(plan_launches(conv_phases(d, 1), d->nsub, launches, p), "conv1d_bwd_data_tc: phases exceed kernel limits");
+  for (const TcParams& lp : launches) {
+    int rc = run_tc(lp, st);
     if (rc) return rc;
   }
   return KT_OK;
