@@ -302,8 +302,11 @@ def main():
         "losses": {"generator": g_loss, "discriminator": d_loss},
     }
 
-    if rank == 0 and not args.no_roofline:
-        line["roofline"], line["kernel_shares"] = roofline_leg(step, (y_d, x_d), ops, ms_per_step)
+    if not args.no_roofline:
+        # every rank runs the instrumented step (it contains the gradient all-reduces); rank 0 reports
+        roof, shares = roofline_leg(step, (y_d, x_d), ops, ms_per_step)
+        if rank == 0:
+            line["roofline"], line["kernel_shares"] = roof, shares
     if world > 1:
         dist.barrier()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
