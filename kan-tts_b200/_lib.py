@@ -127,5 +127,12 @@ def ptr(t):
     return t.data_ptr()
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def stream_ptr():
+    """cudaStream_t of the calling thread's current stream (raw accessor: ~15x cheaper than
+    torch.cuda.current_stream(), which matters at ~3000 library calls per train step)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream

@@ -75,10 +75,11 @@ def _sig(spec, d):
 
 
 class _timed:
-    __slots__ = ("name", "flops", "nbytes", "e0", "detail")
+    """Context manager around one library call; a no-op unless the profiler is on."""
+    __slots__ = ("name", "spec", "d", "e0")
 
-    def __init__(self, name, flops=0.0, nbytes=0.0, detail=""):
-        self.name, self.flops, self.nbytes, self.detail = name, flops, nbytes, detail
+    def __init__(self, name, spec=None, d=None):
+        self.name, self.spec, self.d = name, spec, d
 
     def __enter__(self):
         if _profiler is not None:
@@ -90,8 +91,9 @@ class _timed:
         if _profiler is not None:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
-            _profiler.records.append((self.name, self.e0, e1, self.flops, self.nbytes))
-            _profiler.details.append(self.detail)
+            flops, nbytes = _conv_work(self.spec, self.d) if self.spec is not None else (0.0, 0.0)
+            _profiler.records.append((self.name, self.e0, e1, flops, nbytes))
+            _profiler.details.append(_sig(self.spec, self.d) if self.spec is not None else "")
         return False
 
 
@@ -280,16 +282,16 @@ class ConvFn(torch.autograd.Function):
             assert resid.shape == y.shape, (resid.shape, y.shape)
         bd = None if bias is None else bias.detach()
         nt = _tc_tile(lib, spec, d, 0)
-        flops, nbytes = _conv_work(spec, d)
+        pass  # (algorithmic work is computed lazily by _timed when the profiler is on)
         if nt:
             global _tc_launches
             img = pw.tc_image(spec, d, 0, nt)
-            with _timed("conv_fwd_tc", flops, nbytes, _sig(spec, d)):
+            with _timed("conv_fwd_tc", spec, d):
                 check(lib.kt_conv1d_fwd_tc(ctypes.byref(d), ptr(x), ptr(img), ptr(bd), ptr(resid),
                                            ptr(y), stream_ptr()), "kt_conv1d_fwd_tc")
             _tc_launches += spec.stride if spec.transposed else 1
         else:
-            with _timed("conv_fwd_ffma", flops, nbytes, _sig(spec, d)):
+            with _timed("conv_fwd_ffma", spec, d):
                 check(lib.kt_conv1d_fwd(ctypes.byref(d), ptr(x), ptr(pw.w_fwd), ptr(bd), ptr(resid), ptr(y),
                                         stream_ptr()), "kt_conv1d_fwd")
         _count(spec.stride if spec.transposed else 1)
@@ -312,15 +314,15 @@ class ConvFn(torch.autograd.Function):
         dx = dres = dbias = dv = dg = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            flops, nbytes = _conv_work(spec, d)
+            pass  # (algorithmic work is computed lazily by _timed when the profiler is on)
             if ctx.nt_bwd:
                 global _tc_launches
-                with _timed("conv_dgrad_tc", flops, nbytes, _sig(spec, d)):
+                with _timed("conv_dgrad_tc", spec, d):
                     check(lib.kt_conv1d_bwd_data_tc(ctypes.byref(d), ptr(dy), ptr(y), ptr(ctx.img_bwd), ptr(x),
                                                     ptr(dx), st), "kt_conv1d_bwd_data_tc")
                 _tc_launches += 1
             else:
-                with _timed("conv_dgrad_ffma", flops, nbytes, _sig(spec, d)):
+                with _timed("conv_dgrad_ffma", spec, d):
                     check(lib.kt_conv1d_bwd_data(ctypes.byref(d), ptr(dy), ptr(y), ptr(ctx.w_bwd), ptr(x), ptr(dx),
                                                  st), "kt_conv1d_bwd_data")
             _count(max(spec.stride if not spec.transposed else 1, spec.upsample))
@@ -332,16 +334,16 @@ class ConvFn(torch.autograd.Function):
             dw = torch.empty(spec.w_numel, device=x.device, dtype=torch.float32)
             if need_b:
                 dbias = torch.empty(spec.c_out, device=x.device, dtype=torch.float32)
-            flops, nbytes = _conv_work(spec, d)
+            pass  # (algorithmic work is computed lazily by _timed when the profiler is on)
             ws_floats = _wgrad_tc_workspace(lib, spec, d)
             if ws_floats:
                 ws = torch.empty(ws_floats, device=x.device, dtype=torch.float32)
-                with _timed("conv_wgrad_tc", flops, nbytes, _sig(spec, d)):
+                with _timed("conv_wgrad_tc", spec, d):
                     check(lib.kt_conv1d_bwd_weight_tc(ctypes.byref(d), ptr(x), ptr(dy), ptr(y), ptr(dw), ptr(dbias),
                                                       ptr(ws), ws_floats, st), "kt_conv1d_bwd_weight_tc")
                 _tc_launches += 1
             else:
-                with _timed("conv_wgrad_ffma", flops, nbytes, _sig(spec, d)):
+                with _timed("conv_wgrad_ffma", spec, d):
                     check(lib.kt_conv1d_bwd_weight(ctypes.byref(d), ptr(x), ptr(dy), ptr(y), ptr(dw), ptr(dbias), st),
                           "kt_conv1d_bwd_weight")
             _count(4 if need_b else 2)
