@@ -183,6 +183,76 @@ struct RowMap {
   }
 };
 
+// Implementation for one (VEC, AUX) combination.  Phase 1 issues ALL global loads of a batch (NB rows x
+// 32 bytes, x2 with an aux tensor) back to back with no dependent instruction in between; phase 2
+// converts and stores.  The two phases are separate fully-unrolled loops without early exits: with one
+// CTA per SM the staging loop is pure DRAM/L2 latency, and a fused load->convert->store loop measured
+// ~1 load in flight per thread (profiles/r01_notes.md).
+template <int NB, bool VEC, bool AUX>
+__device__ __forceinline__ void stage_rows_impl(uint8_t* img_hi, uint8_t* img_lo, const Side& s, const float* base,
+                                                const float* aux_base, int c_total, int ch0, int nv, const RowMap& rm,
+                                                int rows, int tid) {
+  const int q = tid & 7;
+  for (int r0 = tid >> 3; r0 < rows; r0 += 16 * NB) {
+    float4 v[NB][2], a[NB][2];
+    long long off[NB];
+    bool ok[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int r = r0 + 16 * i;
+      long long srow = 0;
+      ok[i] = r < rows && nv > 0 && rm.map(r, srow);
+      off[i] = ok[i] ? srow * c_total + ch0 + q * 8 : 0;   // offset 0 is always a readable address
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      if constexpr (VEC) {
+        v[i][0] = __ldg(reinterpret_cast<const float4*>(base + off[i]));
+        v[i][1] = __ldg(reinterpret_cast<const float4*>(base + off[i] + 4));
+        if constexpr (AUX) {
+          a[i][0] = __ldg(reinterpret_cast<const float4*>(aux_base + off[i]));
+          a[i][1] = __ldg(reinterpret_cast<const float4*>(aux_base + off[i] + 4));
+        }
+      } else {
+        float t[8], u[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const long long oe = (ok[i] && e < nv) ? off[i] + e : 0;
+          t[e] = __ldg(base + oe);
+          u[e] = AUX ? __ldg(aux_base + oe) : 0.f;
+          if (!(ok[i] && e < nv)) { t[e] = 0.f; u[e] = 0.f; }
+        }
+        v[i][0] = make_float4(t[0], t[1], t[2], t[3]); v[i][1] = make_float4(t[4], t[5], t[6], t[7]);
+        a[i][0] = make_float4(u[0], u[1], u[2], u[3]); a[i][1] = make_float4(u[4], u[5], u[6], u[7]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int r = r0 + 16 * i;
+      float x[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
+      if (VEC && !ok[i]) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = 0.f;
+      }
+      if (s.mode == SIDE_LRELU) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = x[e] > 0.f ? x[e] : x[e] * s.slope;
+      } else if (AUX) {
+        const float ax[8] = {a[i][0].x, a[i][0].y, a[i][0].z, a[i][0].w, a[i][1].x, a[i][1].y, a[i][1].z, a[i][1].w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = side_apply(x[e], ax[e], s.mode, s.slope);
+      }
+      uint4 hi, lo;
+      tc::split8(x, hi, lo);
+      if (r < rows) {
+        const uint32_t o = tc::sw128_offset((uint32_t)r, (uint32_t)q);
+        *reinterpret_cast<uint4*>(img_hi + o) = hi;
+        *reinterpret_cast<uint4*>(img_lo + o) = lo;
+      }
+    }
+  }
+}
+
 template <int NB>
 __device__ __forceinline__ void stage_rows(uint8_t* img_hi, uint8_t* img_lo, const Side& s, const float* base,
                                            const float* aux_base, int c_total, int ch0, int c_valid, bool fill_all,
@@ -196,52 +266,12 @@ __device__ __forceinline__ void stage_rows(uint8_t* img_hi, uint8_t* img_lo, con
   const int nv = min(8, c_valid - q * 8);                       // valid channels of this thread's chunk (may be <= 0)
   const bool vec = nv == 8 && (c_total & 3) == 0 && ((ch0 + q * 8) & 3) == 0;
   const bool has_aux = s.mode >= SIDE_DLRELU;
-  for (int r0 = tid >> 3; r0 < rows; r0 += 16 * NB) {
-    float4 v[NB][2], a[NB][2];
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-      const int r = r0 + 16 * i;
-      long long srow = 0;
-      const bool ok = r < rows && nv > 0 && rm.map(r, srow);
-      const long long off = ok ? srow * c_total + ch0 + q * 8 : 0;
-      if (vec) {
-        v[i][0] = ok ? __ldg(reinterpret_cast<const float4*>(base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[i][1] = ok ? __ldg(reinterpret_cast<const float4*>(base + off + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_aux) {
-          a[i][0] = ok ? __ldg(reinterpret_cast<const float4*>(aux_base + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          a[i][1] = ok ? __ldg(reinterpret_cast<const float4*>(aux_base + off + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      } else {
-        float t[8], u[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const bool oe = ok && e < nv;
-          t[e] = oe ? __ldg(base + off + e) : 0.f;
-          u[e] = (oe && has_aux) ? __ldg(aux_base + off + e) : 0.f;
-        }
-        v[i][0] = make_float4(t[0], t[1], t[2], t[3]); v[i][1] = make_float4(t[4], t[5], t[6], t[7]);
-        a[i][0] = make_float4(u[0], u[1], u[2], u[3]); a[i][1] = make_float4(u[4], u[5], u[6], u[7]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-      const int r = r0 + 16 * i;
-      if (r >= rows) break;
-      float x[8] = {v[i][0].x, v[i][0].y, v[i][0].z, v[i][0].w, v[i][1].x, v[i][1].y, v[i][1].z, v[i][1].w};
-      if (s.mode == SIDE_LRELU) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) x[e] = x[e] > 0.f ? x[e] : x[e] * s.slope;
-      } else if (has_aux) {
-        const float ax[8] = {a[i][0].x, a[i][0].y, a[i][0].z, a[i][0].w, a[i][1].x, a[i][1].y, a[i][1].z, a[i][1].w};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) x[e] = side_apply(x[e], ax[e], s.mode, s.slope);
-      }
-      uint4 hi, lo;
-      tc::split8(x, hi, lo);
-      const uint32_t o = tc::sw128_offset((uint32_t)r, (uint32_t)q);
-      *reinterpret_cast<uint4*>(img_hi + o) = hi;
-      *reinterpret_cast<uint4*>(img_lo + o) = lo;
-    }
+  if (vec) {
+    if (has_aux) stage_rows_impl<NB, true, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
+    else stage_rows_impl<NB, true, false>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
+  } else {
+    if (has_aux) stage_rows_impl<2, false, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
+    else stage_rows_impl<2, false, false>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
   }
 }
 
