@@ -3,6 +3,7 @@
 unmodified reference.  Tolerances (north_star): waveform RMS <= 1e-3, mel-L1 <= 1e-4; we hold the
 exact-fp32 (FFMA) kernels to ~1e-5 relative and the tcgen05 bf16x3 kernels to 1e-4 relative."""
 import math
+import zlib
 
 import pytest
 import torch
@@ -73,7 +74,7 @@ def _run_case(name, force_ffma):
         spec.act_out = KT_ACT_TANH
     elif act_out is not None:
         spec.act_out, spec.act_out_slope = KT_ACT_LRELU, act_out
-    g = torch.Generator().manual_seed(hash(name) % 10000)
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) % 10000)   # deterministic across processes
     wshape = (spec.c_in, spec.c_out, spec.kernel) if spec.transposed else (spec.c_out, spec.c_in // spec.groups, spec.kernel)
     v = torch.randn(wshape, generator=g) * 0.3
     gg = (v.norm(2, dim=(1, 2), keepdim=True) * (1 + 0.2 * torch.randn(wshape[0], 1, 1, generator=g))) if wn else None
@@ -94,7 +95,6 @@ def _run_case(name, force_ffma):
                             pad_right=spec.pad_right, groups=spec.groups, transposed=spec.transposed,
                             upsample=spec.upsample, crop=spec.crop, act_in=act_in, act_out=act_out)
     assert tuple(yo.shape) == ys, (yo.shape, ys)
-    (yo * r).sum().backward()
 
     # product (GPU, through the C ABI)
     ops.set_force_ffma(force_ffma)
@@ -105,16 +105,23 @@ def _run_case(name, force_ffma):
         rg = _to_rows(resid).to(DEV).requires_grad_(True) if use_resid else None
         tc0 = ops.tc_launch_count()
         y = ops.conv(xg, spec, ops.PreparedWeight(), vg, g2, bg, rg)
+        # A fused output LeakyReLU makes the backward mask depend on sign(pre-activation).  The handful of
+        # outputs whose sign differs between the two forwards (|y| below the forward error) would change the
+        # gradient discontinuously: exclude exactly those outputs from the scalar both sides differentiate.
+        if act_out is not None and act_out != "tanh":
+            res_o = ro.detach() if use_resid else 0.0
+            res_g = _from_rows(rg.detach()).cpu() if use_resid else 0.0
+            flip = torch.sign(yo.detach() - res_o) != torch.sign(_from_rows(y.detach()).cpu() - res_g)
+            assert float(flip.float().mean()) < 1e-3
+            r = r * (~flip)
+        (yo * r).sum().backward()
         (y * _to_rows(r).to(DEV)).sum().backward()
         used_tc = ops.tc_launch_count() > tc0
     finally:
         ops.set_force_ffma(False)
     tol = 1e-4 if used_tc else 2e-5
     assert rel_l2(_from_rows(y).cpu(), yo) < tol, ("y", rel_l2(_from_rows(y).cpu(), yo))
-    # a fused output LeakyReLU makes the backward mask depend on sign(y): the handful of |y| ~ 1e-5 elements
-    # whose sign differs between the bf16x3 and the fp32 forward change dpre discontinuously
-    tol_dx = 5e-4 if (used_tc and act_out is not None) else tol
-    assert rel_l2(_from_rows(xg.grad).cpu(), xo.grad) < tol_dx, ("dx", rel_l2(_from_rows(xg.grad).cpu(), xo.grad))
+    assert rel_l2(_from_rows(xg.grad).cpu(), xo.grad) < tol, ("dx", rel_l2(_from_rows(xg.grad).cpu(), xo.grad))
     tol_w = 3e-4 if used_tc else 5e-5
     assert rel_l2(vg.grad.cpu(), vo.grad) < tol_w, ("dv", rel_l2(vg.grad.cpu(), vo.grad))
     assert rel_l2(bg.grad.cpu(), bo.grad) < tol_w, "dbias"
