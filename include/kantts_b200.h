@@ -178,6 +178,71 @@ int kt_stft_mel_bwd(const KtMelDesc* d, const float* dmel, const float* damp, co
 /* out[0] = scale * sum |a - b|  (F.l1_loss numerator; loss.py:249,309); out[0] is overwritten. */
 int kt_l1_sum(const float* a, const float* b, int64_t n, float scale, float* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * SAM-BERT acoustic model (kantts/models/sambert).  Activations are (B, L, C) rows -- the
+ * reference's own layout for this model -- so nn.Linear and the transposed nn.Conv1d pairs
+ * (sambert/__init__.py:140-149, fsmn.py:36-43) are kt_conv1d_* calls with nsub = 1 and
+ * kernel 1 / 3 / 9; the entry points below cover what is not a convolution.
+ * --------------------------------------------------------------------------------------------- */
+
+/* nn.LayerNorm(C, eps) over the last dim (sambert/__init__.py:64,131,197; kantts_sambert.py:58,129).
+ * x, y, dx: [rows][C]; mean / rstd: [rows] (saved for backward); 1 <= C <= 1024.
+ * Backward needs kt_layernorm_bwd_workspace(rows, C) floats of workspace (partial column sums). */
+int kt_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                     int32_t rows, int32_t c, float eps, void* stream);
+int64_t kt_layernorm_bwd_workspace(int32_t rows, int32_t c);
+int kt_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                     float* dx, float* dgamma, float* dbeta, float* workspace, int64_t workspace_floats,
+                     int32_t rows, int32_t c, void* stream);
+
+/* ScaledDotProductAttention over all heads (sambert/__init__.py:17-29 plus the head split / merge of
+ * :80-100 and :278-300).  q, k, v and out are row tensors addressed as
+ *     q[(b*lq + i)*q_stride + h*d_head + e]      (same for k / v over lk rows, out over lq rows)
+ * so the fused QKV projection output is consumed in place (pass base pointers offset to the q / k / v column
+ * blocks) and `out` is the merged-heads (B, Lq, H*d_head) tensor.  probs [(h*B + b)][lq][lk] is the
+ * reference's returned `attn` (head-major) and is always written (backward reads it).
+ * mask: optional uint8, non-zero = masked (-inf before the softmax), element
+ *     mask[b*mask_b_stride + i*mask_q_stride + j]   (mask_q_stride 0 = key-padding mask broadcast over queries).
+ * d_head in {8, 16, 32, 64}; lk <= 2048. */
+typedef struct KtAttnDesc {
+  int32_t batch, heads, d_head, lq, lk;
+  int32_t q_stride, k_stride, v_stride, o_stride; /* floats between consecutive rows */
+  int32_t mask_q_stride;
+  int64_t mask_b_stride;
+  float scale;                                    /* 1 / temperature = d_head ** -0.5 */
+  float keep_scale;                               /* attention dropout: 1 / (1 - p); used only with a keep mask */
+} KtAttnDesc;
+/* keep: optional attention-dropout keep mask, uint8 [(h*B + b)][lq][lk] (non-zero = kept; nn.Dropout on the
+ * probabilities, sambert/__init__.py:26).  `probs` always receives the UNdropped softmax (backward needs it);
+ * probs_dropped (optional) receives keep * probs * keep_scale, i.e. the tensor the reference returns as `attn`
+ * in training mode. */
+int kt_attention_fwd(const KtAttnDesc* d, const float* q, const float* k, const float* v, const uint8_t* mask,
+                     const uint8_t* keep, float* out, float* probs, float* probs_dropped, void* stream);
+/* dq / dk / dv use the strides of q / k / v (so they can be the column blocks of one d(QKV) tensor); dout uses
+ * o_stride.  delta: [heads*batch*lq] floats of scratch.  accum_dq != 0: dq += (PNCA: the x- and h-attention
+ * share their queries, sambert/__init__.py:283,293). */
+int kt_attention_bwd(const KtAttnDesc* d, const float* q, const float* k, const float* v, const float* probs,
+                     const uint8_t* keep, const float* dout, float* dq, float* dk, float* dv, float* delta,
+                     int32_t accum_dq, void* stream);
+
+/* FSMN MemoryBlockV2 (fsmn.py:46-77): y = keep * (xm + depthwise_conv(pad(xm, lp, K-1-lp))), xm = x * keep,
+ * keep = !mask.  x, y [B][T][C]; w [C][K] (the (C,1,K) conv_dw weight); mask optional uint8 [B][T], non-zero = padding.
+ * Backward: dx and / or dw (either may be NULL); dw needs kt_fsmn_bwd_workspace floats. */
+int kt_fsmn_fwd(const float* x, const float* w, const uint8_t* mask, float* y, int32_t batch, int32_t t, int32_t c,
+                int32_t k, int32_t pad_left, void* stream);
+int64_t kt_fsmn_bwd_workspace(int32_t batch, int32_t t, int32_t c, int32_t k);
+int kt_fsmn_bwd(const float* x, const float* dy, const float* w, const uint8_t* mask, float* dx, float* dw,
+                float* workspace, int64_t workspace_floats, int32_t batch, int32_t t, int32_t c, int32_t k,
+                int32_t pad_left, void* stream);
+
+/* LengthRegulator (adaptors.py:15-37) as a row gather: out[b][t][:] = idx[b][t] >= 0 ? in[b][idx[b][t]][:] : 0.
+ * Backward sums, for every input row (b, i), the output rows of its contiguous span
+ * [start[b][i], start[b][i] + count[b][i]) whose idx equals i. */
+int kt_rows_gather_fwd(const float* in, const int32_t* idx, float* out, int32_t batch, int32_t t_out, int32_t t_in,
+                       int32_t c, void* stream);
+int kt_rows_gather_bwd(const float* dout, const int32_t* idx, const int32_t* start, const int32_t* count, float* din,
+                       int32_t batch, int32_t t_out, int32_t t_in, int32_t c, void* stream);
+
 /* library info */
 const char* kt_last_error(void);
 int kt_version(void);

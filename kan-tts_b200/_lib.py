@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkantts_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "conv_ffma.cu", "conv_tc.cu", "wgrad_tc.cu", "weights.cu", "misc.cu", "stft_mel.cu"]
+SOURCES = ["api.cu", "conv_ffma.cu", "conv_tc.cu", "wgrad_tc.cu", "weights.cu", "misc.cu", "stft_mel.cu", "sambert.cu"]
 
 KT_ACT_NONE, KT_ACT_LRELU, KT_ACT_TANH = 0, 1, 2
 KT_PATH_AUTO, KT_PATH_FFMA, KT_PATH_TC = 0, 1, 2
@@ -32,6 +32,12 @@ class KtConv1dDesc(ctypes.Structure):
 class KtMelDesc(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("batch", "t", "n_fft", "hop", "n_mels", "frames", "pad_mode")] + \
                [(n, ctypes.c_float) for n in ("eps", "ref_db", "min_db", "norm_scale", "norm_shift", "norm_lo", "norm_hi")]
+
+
+class KtAttnDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("batch", "heads", "d_head", "lq", "lk", "q_stride", "k_stride",
+                                              "v_stride", "o_stride", "mask_q_stride")] + \
+               [("mask_b_stride", ctypes.c_int64), ("scale", ctypes.c_float), ("keep_scale", ctypes.c_float)]
 
 
 _P = ctypes.c_void_p
@@ -61,6 +67,16 @@ PROTOTYPES = {
     "kt_conv1d_bwd_data_tc": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P],
     "kt_conv1d_bwd_weight_tc_workspace": [ctypes.POINTER(KtConv1dDesc)],
     "kt_conv1d_bwd_weight_tc": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P, _L, _P],
+    "kt_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
+    "kt_layernorm_bwd_workspace": [_I, _I],
+    "kt_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
+    "kt_attention_fwd": [ctypes.POINTER(KtAttnDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "kt_attention_bwd": [ctypes.POINTER(KtAttnDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P],
+    "kt_fsmn_fwd": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "kt_fsmn_bwd_workspace": [_I, _I, _I, _I],
+    "kt_fsmn_bwd": [_P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P],
+    "kt_rows_gather_fwd": [_P, _P, _P, _I, _I, _I, _I, _P],
+    "kt_rows_gather_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "kt_version": [],
     "kt_has_tc": [],
 }

@@ -24,6 +24,20 @@ long long tc_image_bytes(const KtConv1dDesc*, int);
 int tc_pack_layer(const KtConv1dDesc*, int, const float*, void*, cudaStream_t);
 int conv1d_fwd_tc(const KtConv1dDesc*, const float*, const void*, const float*, const float*, float*, cudaStream_t);
 int conv1d_bwd_data_tc(const KtConv1dDesc*, const float*, const float*, const void*, const float*, float*, cudaStream_t);
+int layernorm_fwd(const float*, const float*, const float*, float*, float*, float*, int, int, float, cudaStream_t);
+long long layernorm_bwd_workspace(int, int);
+int layernorm_bwd(const float*, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
+                  long long, int, int, cudaStream_t);
+int attention_fwd(const KtAttnDesc*, const float*, const float*, const float*, const unsigned char*, const unsigned char*,
+                  float*, float*, float*, cudaStream_t);
+int attention_bwd(const KtAttnDesc*, const float*, const float*, const float*, const float*, const unsigned char*,
+                  const float*, float*, float*, float*, float*, int, cudaStream_t);
+int fsmn_fwd(const float*, const float*, const unsigned char*, float*, int, int, int, int, int, cudaStream_t);
+long long fsmn_bwd_workspace(int, int, int, int);
+int fsmn_bwd(const float*, const float*, const float*, const unsigned char*, float*, float*, float*, long long, int, int,
+             int, int, int, cudaStream_t);
+int rows_gather_fwd(const float*, const int*, float*, int, int, int, int, cudaStream_t);
+int rows_gather_bwd(const float*, const int*, const int*, const int*, float*, int, int, int, int, cudaStream_t);
 }  // namespace kt
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
@@ -129,6 +143,46 @@ int kt_conv1d_bwd_data_tc(const KtConv1dDesc* d, const float* dy, const float* y
   if (rc) return rc;
   KT_REQUIRE(dy && wimg && dx, "kt_conv1d_bwd_data_tc: null pointer");
   return kt::conv1d_bwd_data_tc(d, dy, y, wimg, x, dx, ST(stream));
+}
+
+int kt_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,
+                     int32_t rows, int32_t c, float eps, void* stream) {
+  return kt::layernorm_fwd(x, gamma, beta, y, mean, rstd, rows, c, eps, ST(stream));
+}
+int64_t kt_layernorm_bwd_workspace(int32_t rows, int32_t c) { return kt::layernorm_bwd_workspace(rows, c); }
+int kt_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
+                     float* dx, float* dgamma, float* dbeta, float* workspace, int64_t workspace_floats,
+                     int32_t rows, int32_t c, void* stream) {
+  return kt::layernorm_bwd(dy, x, gamma, mean, rstd, dx, dgamma, dbeta, workspace, workspace_floats, rows, c, ST(stream));
+}
+int kt_attention_fwd(const KtAttnDesc* d, const float* q, const float* k, const float* v, const uint8_t* mask,
+                     const uint8_t* keep, float* out, float* probs, float* probs_dropped, void* stream) {
+  return kt::attention_fwd(d, q, k, v, mask, keep, out, probs, probs_dropped, ST(stream));
+}
+int kt_attention_bwd(const KtAttnDesc* d, const float* q, const float* k, const float* v, const float* probs,
+                     const uint8_t* keep, const float* dout, float* dq, float* dk, float* dv, float* delta,
+                     int32_t accum_dq, void* stream) {
+  return kt::attention_bwd(d, q, k, v, probs, keep, dout, dq, dk, dv, delta, accum_dq, ST(stream));
+}
+int kt_fsmn_fwd(const float* x, const float* w, const uint8_t* mask, float* y, int32_t batch, int32_t t, int32_t c,
+                int32_t k, int32_t pad_left, void* stream) {
+  return kt::fsmn_fwd(x, w, mask, y, batch, t, c, k, pad_left, ST(stream));
+}
+int64_t kt_fsmn_bwd_workspace(int32_t batch, int32_t t, int32_t c, int32_t k) {
+  return kt::fsmn_bwd_workspace(batch, t, c, k);
+}
+int kt_fsmn_bwd(const float* x, const float* dy, const float* w, const uint8_t* mask, float* dx, float* dw,
+                float* workspace, int64_t workspace_floats, int32_t batch, int32_t t, int32_t c, int32_t k,
+                int32_t pad_left, void* stream) {
+  return kt::fsmn_bwd(x, dy, w, mask, dx, dw, workspace, workspace_floats, batch, t, c, k, pad_left, ST(stream));
+}
+int kt_rows_gather_fwd(const float* in, const int32_t* idx, float* out, int32_t batch, int32_t t_out, int32_t t_in,
+                       int32_t c, void* stream) {
+  return kt::rows_gather_fwd(in, idx, out, batch, t_out, t_in, c, ST(stream));
+}
+int kt_rows_gather_bwd(const float* dout, const int32_t* idx, const int32_t* start, const int32_t* count, float* din,
+                       int32_t batch, int32_t t_out, int32_t t_in, int32_t c, void* stream) {
+  return kt::rows_gather_bwd(dout, idx, start, count, din, batch, t_out, t_in, c, ST(stream));
 }
 
 }  // extern "C"

@@ -274,3 +274,77 @@ def hifigan_model_builder(config, device, capturable=False):
         else:
             model["discriminator"][name], optimizer["discriminator"][name], scheduler["discriminator"][name] = m, opt, sch
     return model, optimizer, scheduler
+
+
+# ------------------------------------------------------------------------------------------------
+# SAM-BERT
+# ------------------------------------------------------------------------------------------------
+
+
+class NoamLR(torch.optim.lr_scheduler.LRScheduler):
+    """kantts/train/scheduler.py:25-46: lr = base * sqrt(w) * min(step^-0.5, step * w^-1.5)."""
+
+    def __init__(self, optimizer, warmup_steps):
+        self.warmup_steps = warmup_steps
+        super().__init__(optimizer)
+
+    def get_lr(self):
+        step = max(1, self.last_epoch)
+        scale = self.warmup_steps ** 0.5 * min(step ** (-0.5), step * self.warmup_steps ** (-1.5))
+        return [base_lr * scale for base_lr in self.base_lrs]
+
+
+class SambertStep:
+    """``Sambert_Trainer.train_step`` (kantts/train/trainer.py:898-1005): teacher-forced forward, MelReconLoss +
+    ProsodyReconLoss, backward, gradient-norm clipping, Adam, NoamLR.  Data parallel: the batch is sharded by
+    utterance and the only exchange is ONE in-place NCCL all-reduce (mean) of the flat gradient buffer
+    (49.2 MB for sambert_24k.yaml) between backward and the clip -- replacing the DistributedDataParallel
+    wrapper of kantts/models/__init__.py:120-127.  Losses stay on the device (``losses_to_float`` syncs)."""
+
+    def __init__(self, model, optimizer, scheduler, criterion, grad_clip=1.0):
+        self.model, self.optimizer, self.scheduler, self.criterion = model, optimizer, scheduler, criterion
+        self.grad_clip = grad_clip
+        self.grads = FlatGrads(model)
+        self.steps = 0
+
+    def step(self, batch):
+        """batch: dict with the reference collate keys (input_lings, input_emotions, input_speakers,
+        valid_input_lengths, valid_output_lengths, mel_targets, durations, pitch_contours, energy_contours),
+        tensors already on the model's device."""
+        res = self.model(
+            batch["input_lings"], batch["input_emotions"], batch["input_speakers"], batch["valid_input_lengths"],
+            output_lengths=batch["valid_output_lengths"], mel_targets=batch["mel_targets"],
+            duration_targets=batch["durations"], pitch_targets=batch["pitch_contours"],
+            energy_targets=batch["energy_contours"])
+        mel_loss_, mel_loss = self.criterion["MelReconLoss"](
+            batch["valid_output_lengths"], batch["mel_targets"], res["dec_outputs"], res["postnet_outputs"])
+        dur_loss, pitch_loss, energy_loss = self.criterion["ProsodyReconLoss"](
+            res["valid_inter_lengths"], res["duration_targets"], res["pitch_targets"], res["energy_targets"],
+            res["log_duration_predictions"], res["pitch_predictions"], res["energy_predictions"])
+        loss_total = mel_loss_ + mel_loss + dur_loss + pitch_loss + energy_loss
+        self.grads.zero()
+        loss_total.backward()
+        self.grads.all_reduce_mean()
+        if self.grad_clip is not None:
+            torch.nn.utils.clip_grad_norm_(self.grads.params, self.grad_clip)
+        self.optimizer.step()
+        self.scheduler.step()
+        self.steps += 1
+        return {"TotalLoss": loss_total.detach(), "mel_loss_": mel_loss_.detach(), "mel_loss": mel_loss.detach(),
+                "dur_loss": dur_loss.detach(), "pitch_loss": pitch_loss.detach(),
+                "energy_loss": energy_loss.detach(), "x_band_width": res["x_band_width"],
+                "h_band_width": res["h_band_width"]}
+
+
+def sambert_model_builder(config, device):
+    """kantts/models/__init__.py:89-129 without the DDP wrapper: ``config`` is the whole yaml dict with the
+    linguistic-unit sizes already merged into ``Model.KanTtsSAMBERT.params`` (bin/train_sambert.py:144-146)."""
+    from . import sambert
+    sect = config["Model"]["KanTtsSAMBERT"]
+    model = sambert.KanTtsSAMBERT(sect["params"]).to(device)
+    opt = optimizer_builder(model.parameters(), sect["optimizer"].get("type", "Adam"),
+                            dict(sect["optimizer"].get("params", {})))
+    sch_t = sect["scheduler"].get("type", "NoamLR")
+    sch_p = sect["scheduler"].get("params", {})
+    sch = NoamLR(opt, **sch_p) if sch_t == "NoamLR" else getattr(torch.optim.lr_scheduler, sch_t)(opt, **sch_p)
+    return model, opt, sch

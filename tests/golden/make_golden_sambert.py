@@ -19,8 +19,10 @@ import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, HERE)
 
 from oracle.ref_shims import import_reference  # noqa: E402
+from make_batch import make_sambert_batch as make_batch  # noqa: E402
 
 import_reference()
 from kantts.models.sambert.kantts_sambert import KanTtsSAMBERT  # noqa: E402
@@ -40,29 +42,6 @@ SMALL_CFG = dict(
     postnet_ffn_inner_dim=24, postnet_dropout=0.1, postnet_shift=1, postnet_lstm_units=8, MAS=False,
     sy=20, tone=5, syllable_flag=4, word_segment=4, emotion=3, speaker=2,
 )
-
-
-def make_batch(cfg, B, L, gen, short=2):
-    """Synthetic teacher-forcing batch shaped like the collate output of the reference dataset:
-    durations of the padded symbols are 0, every row's durations sum to its output length and the
-    padded mel length is a multiple of outputs_per_step."""
-    r = cfg["outputs_per_step"]
-    ling = torch.stack([torch.randint(0, cfg[k], (B, L), generator=gen)
-                        for k in ("sy", "tone", "syllable_flag", "word_segment")], -1)
-    emo = torch.randint(0, cfg["emotion"], (B, L), generator=gen)
-    spk = torch.randint(0, cfg["speaker"], (B, L), generator=gen)
-    in_len = torch.tensor([L - short * (i % 2) for i in range(B)])
-    dur = torch.randint(1, 5, (B, L), generator=gen)
-    dur = dur * (torch.arange(L)[None, :] < in_len[:, None])
-    # make row 0 the longest and its length a multiple of r
-    dur[0, 0] += (-int(dur[0].sum())) % r + r
-    out_len = dur.sum(1)
-    T = int(out_len.max())
-    assert T % r == 0 and int(out_len[0]) == T
-    return dict(
-        inputs_ling=ling, inputs_emotion=emo, inputs_speaker=spk, input_lengths=in_len, output_lengths=out_len,
-        mel_targets=torch.randn(B, T, cfg["num_mels"], generator=gen), duration_targets=dur,
-        pitch_targets=torch.randn(B, L, generator=gen), energy_targets=torch.randn(B, L, generator=gen))
 
 
 def main():
