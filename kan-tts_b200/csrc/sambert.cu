@@ -171,7 +171,11 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, float* 
 template <int NC>
 static int ln_bwd_launch(const float* dy, const float* x, const float* g, const float* mean, const float* rstd,
                          float* dx, float* ws, int rows, int c, int grid, cudaStream_t st) {
-  layernorm_bwd_kernel<NC><<<grid, 256, 8 * 2 * c * sizeof(float), st>>>(dy, x, g, mean, rstd, dx, ws, rows, c);
+  const size_t smem = (size_t)8 * 2 * c * sizeof(float);   // up to 64 KB at C = 1024: above the 48 KB default
+  static std::atomic<bool> attr_set{false};
+  if (smem > 48 * 1024 && !attr_set.exchange(true))
+    KT_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  layernorm_bwd_kernel<NC><<<grid, 256, smem, st>>>(dy, x, g, mean, rstd, dx, ws, rows, c);
   KT_CHECK_CUDA(cudaGetLastError());
   return KT_OK;
 }
@@ -218,58 +222,108 @@ struct AttnArgs {
   long long mask_b_stride;
   int mask_q_stride;
   float scale;
-  int rows_per_warp;
 };
 
-template <int D>
+// Sum N per-lane partials across the warp so that every element ends up, fully reduced, in exactly one lane:
+// N >= 32: lane l holds elements [l*N/32, (l+1)*N/32) in v[0 .. N/32);  N == 16: lanes 2m and 2m+1 hold element m
+// in v[0].  N-1 shuffles instead of 5*N for a butterfly per element.
+template <int n, int N>
+__device__ __forceinline__ void rs_stage(float (&v)[N], int lane, int off) {
+  if constexpr (n >= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = upper ? v[i] : v[i + n];
+      const float keep = upper ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  } else {
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], off);
+  }
+}
+template <int N>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[N], int lane) {
+  rs_stage<N / 2>(v, lane, 16);
+  rs_stage<N / 4>(v, lane, 8);
+  rs_stage<N / 8>(v, lane, 4);
+  rs_stage<N / 16>(v, lane, 2);
+  rs_stage<N / 32>(v, lane, 1);
+}
+
+// cooperative copy of nk rows of D floats (row stride `stride` floats) into shared rows of DP floats
+template <int D, int DP>
+__device__ __forceinline__ void stage_rows_smem(float* dst, const float* src, int nk, int stride) {
+  const bool vec = (stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  if (vec) {
+    for (int i = threadIdx.x; i < nk * (D / 4); i += blockDim.x) {
+      const int j = i / (D / 4), e = i % (D / 4);
+      *reinterpret_cast<float4*>(dst + j * DP + 4 * e) =
+          __ldg(reinterpret_cast<const float4*>(src + (long long)j * stride) + e);
+    }
+  } else {
+    for (int i = threadIdx.x; i < nk * D; i += blockDim.x) {
+      const int j = i / D, d = i % D;
+      dst[j * DP + d] = __ldg(src + (long long)j * stride + d);
+    }
+  }
+}
+
+// Forward.  CTA = 8 warps x RW query rows of one (batch, head); lanes run over the keys.  A key / value row is
+// read from shared memory once (D/4 LDS.128, rows padded to D+4 floats: conflict-free) and used for all RW rows.
+template <int D, int RW>
 __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnArgs a) {
-  extern __shared__ float sm[];
-  constexpr int DP = D + 1;
-  const int QT = 8 * a.rows_per_warp;
-  float* s_sc = sm;                         // [QT][Lk]  scores -> probabilities
-  float* s_kv = sm + (size_t)QT * a.Lk;     // [kKeyTile][DP]
-  float* s_q = s_kv + kKeyTile * DP;        // [QT][D]
+  extern __shared__ __align__(16) float sm[];
+  constexpr int DP = D + 4;
+  constexpr int QT = 8 * RW;
+  constexpr int N = RW * D;
+  float* s_kv = sm;                        // [kKeyTile][DP]
+  float* s_sc = sm + kKeyTile * DP;        // [QT][Lk]  scores -> probabilities
   const int bh = blockIdx.y, h = bh / a.B, b = bh % a.B;
-  const int q0 = blockIdx.x * QT;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r0 = blockIdx.x * QT + w * RW;          // first query row of this warp
   const float* qb = a.q + (long long)b * a.Lq * a.q_stride + h * D;
   const float* kb = a.k + (long long)b * a.Lk * a.k_stride + h * D;
   const float* vb = a.v + (long long)b * a.Lk * a.v_stride + h * D;
-  for (int i = threadIdx.x; i < QT * D; i += blockDim.x) {
-    const int r = i / D, d = i % D;
-    s_q[i] = (q0 + r < a.Lq) ? __ldg(qb + (long long)(q0 + r) * a.q_stride + d) * a.scale : 0.f;
-  }
-  // pass 1: raw scores
-  for (int kt = 0; kt < a.Lk; kt += kKeyTile) {
-    const int nk = min(kKeyTile, a.Lk - kt);
-    __syncthreads();
-    for (int i = threadIdx.x; i < nk * D; i += blockDim.x) {
-      const int j = i / D, d = i % D;
-      s_kv[j * DP + d] = __ldg(kb + (long long)(kt + j) * a.k_stride + d);
+  float* sc0 = s_sc + (size_t)(w * RW) * a.Lk;
+  {
+    float qr[RW][D];
+#pragma unroll
+    for (int rr = 0; rr < RW; ++rr) {
+      const int r = min(r0 + rr, a.Lq - 1);
+#pragma unroll
+      for (int d = 0; d < D; ++d) qr[rr][d] = __ldg(qb + (long long)r * a.q_stride + d) * a.scale;
     }
-    __syncthreads();
-    for (int rr = 0; rr < a.rows_per_warp; ++rr) {
-      const int r = w * a.rows_per_warp + rr;
-      if (q0 + r >= a.Lq) break;
-      float qr[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) qr[d] = s_q[r * D + d];
-      const unsigned char* mrow = a.mask ? a.mask + b * a.mask_b_stride + (long long)(q0 + r) * a.mask_q_stride : nullptr;
+    for (int kt = 0; kt < a.Lk; kt += kKeyTile) {
+      const int nk = min(kKeyTile, a.Lk - kt);
+      __syncthreads();
+      stage_rows_smem<D, DP>(s_kv, kb + (long long)kt * a.k_stride, nk, a.k_stride);
+      __syncthreads();
       for (int j = lane; j < nk; j += 32) {
-        float acc = 0.f;
+        float kk[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) acc = fmaf(qr[d], s_kv[j * DP + d], acc);
-        if (mrow && mrow[kt + j]) acc = -INFINITY;
-        s_sc[(size_t)r * a.Lk + kt + j] = acc;
+        for (int e = 0; e < D / 4; ++e) {
+          const float4 t = *reinterpret_cast<const float4*>(s_kv + j * DP + 4 * e);
+          kk[4 * e] = t.x; kk[4 * e + 1] = t.y; kk[4 * e + 2] = t.z; kk[4 * e + 3] = t.w;
+        }
+#pragma unroll
+        for (int rr = 0; rr < RW; ++rr) {
+          float acc = 0.f;
+#pragma unroll
+          for (int d = 0; d < D; ++d) acc = fmaf(qr[rr][d], kk[d], acc);
+          if (a.mask) {
+            const int r = min(r0 + rr, a.Lq - 1);
+            if (a.mask[b * a.mask_b_stride + (long long)r * a.mask_q_stride + kt + j]) acc = -INFINITY;
+          }
+          sc0[(size_t)rr * a.Lk + kt + j] = acc;
+        }
       }
     }
   }
   __syncwarp();
   // softmax per row (each warp owns its rows), probabilities to HBM
-  for (int rr = 0; rr < a.rows_per_warp; ++rr) {
-    const int r = w * a.rows_per_warp + rr;
-    if (q0 + r >= a.Lq) break;
-    float* sc = s_sc + (size_t)r * a.Lk;
+  for (int rr = 0; rr < RW; ++rr) {
+    const int r = r0 + rr;
+    float* sc = sc0 + (size_t)rr * a.Lk;
     float m = -INFINITY;
     for (int j = lane; j < a.Lk; j += 32) m = fmaxf(m, sc[j]);
     m = warp_max(m);
@@ -281,63 +335,50 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(AttnArgs a) {
     }
     s = warp_sum(s);
     const float inv = 1.f / s;
-    const long long prow = ((long long)bh * a.Lq + q0 + r) * a.Lk;
-    float* pr = a.probs + prow;
+    const bool live = r < a.Lq;
+    const long long prow = ((long long)bh * a.Lq + (live ? r : 0)) * a.Lk;
     for (int j = lane; j < a.Lk; j += 32) {
       float p = sc[j] * inv;
-      pr[j] = p;
+      if (live) a.probs[prow + j] = p;
       if (a.keep) {
         p = a.keep[prow + j] ? p * a.keep_scale : 0.f;
-        if (a.probs_dropped) a.probs_dropped[prow + j] = p;
+        if (live && a.probs_dropped) a.probs_dropped[prow + j] = p;
       }
       sc[j] = p;
     }
   }
-  // pass 2: out = P V.  Lane l owns dims (l % D)[+32..] of key subset l / D.
-  constexpr int G = D >= 32 ? 1 : 32 / D;       // key subsets per warp
-  constexpr int DPL = D > 32 ? D / 32 : 1;      // dims per lane
-  const int dim0 = D >= 32 ? lane : lane % D;
-  const int sub = D >= 32 ? 0 : lane / D;
-  float acc[4][DPL];
+  // out = P V: per-lane partial sums over the lane's keys for all RW x D outputs, then one reduce-scatter
+  float acc[N];
 #pragma unroll
-  for (int rr = 0; rr < 4; ++rr)
-#pragma unroll
-    for (int e = 0; e < DPL; ++e) acc[rr][e] = 0.f;
+  for (int i = 0; i < N; ++i) acc[i] = 0.f;
   for (int kt = 0; kt < a.Lk; kt += kKeyTile) {
     const int nk = min(kKeyTile, a.Lk - kt);
     __syncthreads();
-    for (int i = threadIdx.x; i < nk * D; i += blockDim.x) {
-      const int j = i / D, d = i % D;
-      s_kv[j * DP + d] = __ldg(vb + (long long)(kt + j) * a.v_stride + d);
-    }
+    stage_rows_smem<D, DP>(s_kv, vb + (long long)kt * a.v_stride, nk, a.v_stride);
     __syncthreads();
+    for (int j = lane; j < nk; j += 32) {
+      float vv[D];
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      if (rr >= a.rows_per_warp) break;
-      const int r = w * a.rows_per_warp + rr;
-      if (q0 + r >= a.Lq) break;
-      const float* sc = s_sc + (size_t)r * a.Lk + kt;
-      for (int j = sub; j < nk; j += G) {
-        const float p = sc[j];
+      for (int e = 0; e < D / 4; ++e) {
+        const float4 t = *reinterpret_cast<const float4*>(s_kv + j * DP + 4 * e);
+        vv[4 * e] = t.x; vv[4 * e + 1] = t.y; vv[4 * e + 2] = t.z; vv[4 * e + 3] = t.w;
+      }
 #pragma unroll
-        for (int e = 0; e < DPL; ++e) acc[rr][e] = fmaf(p, s_kv[j * DP + dim0 + 32 * e], acc[rr][e]);
+      for (int rr = 0; rr < RW; ++rr) {
+        const float p = sc0[(size_t)rr * a.Lk + kt + j];
+#pragma unroll
+        for (int d = 0; d < D; ++d) acc[rr * D + d] = fmaf(p, vv[d], acc[rr * D + d]);
       }
     }
   }
+  warp_reduce_scatter<N>(acc, lane);
+  constexpr int PER = N >= 32 ? N / 32 : 1;
+  const int e0 = N >= 32 ? lane * PER : lane >> 1;
+  const int r = r0 + e0 / D;
+  if (r < a.Lq && (N >= 32 || (lane & 1) == 0)) {
+    float* o = a.out + ((long long)b * a.Lq + r) * a.o_stride + h * D + e0 % D;
 #pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
-    if (rr >= a.rows_per_warp) break;
-    const int r = w * a.rows_per_warp + rr;
-    if (q0 + r >= a.Lq) break;
-#pragma unroll
-    for (int e = 0; e < DPL; ++e) {
-      float t = acc[rr][e];
-      if (G > 1) {
-#pragma unroll
-        for (int o = D; o < 32; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-      }
-      if (sub == 0) a.out[((long long)b * a.Lq + q0 + r) * a.o_stride + h * D + dim0 + 32 * e] = t;
-    }
+    for (int i = 0; i < PER; ++i) o[i] = acc[i];
   }
 }
 
@@ -352,86 +393,110 @@ struct AttnBwdArgs {
   int accum_dq;
 };
 
-// per query row: delta = sum_j P dP,  dQ = scale * sum_j P (dP - delta) K[j],  dP[j] = dO . V[j]
-// one warp per row; lanes over keys, K/V tiles staged in shared memory.
-template <int D>
+// per query row: dP[j] = dO . V[j] (through the dropout), delta = sum_j P dP, dQ = scale * sum_j P (dP - delta) K[j]
+// same work split as the forward kernel: 8 warps x RW rows, lanes over keys, one reduce-scatter for dQ.
+template <int D, int RW>
 __global__ void __launch_bounds__(256) attn_bwd_q_kernel(AttnBwdArgs a) {
-  extern __shared__ float sm[];
-  constexpr int DP = D + 1;
-  float* s_k = sm;                      // [kKeyTile][DP]
-  float* s_v = s_k + kKeyTile * DP;     // [kKeyTile][DP]
-  float* s_dp = s_v + kKeyTile * DP;    // [8][Lk]   dP of the warp's current row
+  extern __shared__ __align__(16) float sm[];
+  constexpr int DP = D + 4;
+  constexpr int QT = 8 * RW;
+  constexpr int N = RW * D;
+  float* s_kv = sm;                       // [kKeyTile][DP]  V, then K
+  float* s_dp = sm + kKeyTile * DP;       // [QT][Lk]
   const int bh = blockIdx.y, h = bh / a.B, b = bh % a.B;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int r = blockIdx.x * 8 + w;
-  const bool live = r < a.Lq;
+  const int r0 = blockIdx.x * QT + w * RW;
   const float* kb = a.k + (long long)b * a.Lk * a.k_stride + h * D;
   const float* vb = a.v + (long long)b * a.Lk * a.v_stride + h * D;
-  float dor[D];
+  float* dp0 = s_dp + (size_t)(w * RW) * a.Lk;
+  long long prow[RW];
+  float delta[RW];
 #pragma unroll
-  for (int d = 0; d < D; ++d)
-    dor[d] = live ? __ldg(a.dout + ((long long)b * a.Lq + r) * a.o_stride + h * D + d) : 0.f;
-  const long long prow = ((long long)bh * a.Lq + (live ? r : 0)) * a.Lk;
-  const float* pr = a.probs + prow;
-  const unsigned char* kr = a.keep ? a.keep + prow : nullptr;
-  float* dp = s_dp + (size_t)w * a.Lk;
-  float delta = 0.f;
+  for (int rr = 0; rr < RW; ++rr) {
+    prow[rr] = ((long long)bh * a.Lq + min(r0 + rr, a.Lq - 1)) * a.Lk;
+    delta[rr] = 0.f;
+  }
+  {
+    float dor[RW][D];
+#pragma unroll
+    for (int rr = 0; rr < RW; ++rr) {
+      const int r = min(r0 + rr, a.Lq - 1);
+#pragma unroll
+      for (int d = 0; d < D; ++d) dor[rr][d] = __ldg(a.dout + ((long long)b * a.Lq + r) * a.o_stride + h * D + d);
+    }
+    for (int kt = 0; kt < a.Lk; kt += kKeyTile) {
+      const int nk = min(kKeyTile, a.Lk - kt);
+      __syncthreads();
+      stage_rows_smem<D, DP>(s_kv, vb + (long long)kt * a.v_stride, nk, a.v_stride);
+      __syncthreads();
+      for (int j = lane; j < nk; j += 32) {
+        float vv[D];
+#pragma unroll
+        for (int e = 0; e < D / 4; ++e) {
+          const float4 t = *reinterpret_cast<const float4*>(s_kv + j * DP + 4 * e);
+          vv[4 * e] = t.x; vv[4 * e + 1] = t.y; vv[4 * e + 2] = t.z; vv[4 * e + 3] = t.w;
+        }
+#pragma unroll
+        for (int rr = 0; rr < RW; ++rr) {
+          float acc = 0.f;
+#pragma unroll
+          for (int d = 0; d < D; ++d) acc = fmaf(dor[rr][d], vv[d], acc);
+          if (a.keep) acc = a.keep[prow[rr] + kt + j] ? acc * a.keep_scale : 0.f;   // d/dP through the dropout
+          dp0[(size_t)rr * a.Lk + kt + j] = acc;
+          delta[rr] = fmaf(__ldg(a.probs + prow[rr] + kt + j), acc, delta[rr]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < RW; ++rr) {
+    delta[rr] = warp_sum(delta[rr]);
+    if (lane == 0 && r0 + rr < a.Lq) a.delta[(long long)bh * a.Lq + r0 + rr] = delta[rr];
+  }
+  float acc[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) acc[i] = 0.f;
   for (int kt = 0; kt < a.Lk; kt += kKeyTile) {
     const int nk = min(kKeyTile, a.Lk - kt);
     __syncthreads();
-    for (int i = threadIdx.x; i < nk * D; i += blockDim.x) {
-      const int j = i / D, d = i % D;
-      s_v[j * DP + d] = __ldg(vb + (long long)(kt + j) * a.v_stride + d);
-    }
+    stage_rows_smem<D, DP>(s_kv, kb + (long long)kt * a.k_stride, nk, a.k_stride);
     __syncthreads();
-    if (live)
-      for (int j = lane; j < nk; j += 32) {
-        float acc = 0.f;
+    for (int j = lane; j < nk; j += 32) {
+      float kk[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) acc = fmaf(dor[d], s_v[j * DP + d], acc);
-        if (kr) acc = kr[kt + j] ? acc * a.keep_scale : 0.f;   // d/dP through the dropout
-        dp[kt + j] = acc;
-        delta = fmaf(__ldg(pr + kt + j), acc, delta);
+      for (int e = 0; e < D / 4; ++e) {
+        const float4 t = *reinterpret_cast<const float4*>(s_kv + j * DP + 4 * e);
+        kk[4 * e] = t.x; kk[4 * e + 1] = t.y; kk[4 * e + 2] = t.z; kk[4 * e + 3] = t.w;
       }
-  }
-  delta = warp_sum(delta);
-  if (live && lane == 0) a.delta[(long long)bh * a.Lq + r] = delta;
-  float dqr[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) dqr[d] = 0.f;
-  for (int kt = 0; kt < a.Lk; kt += kKeyTile) {
-    const int nk = min(kKeyTile, a.Lk - kt);
-    __syncthreads();
-    for (int i = threadIdx.x; i < nk * D; i += blockDim.x) {
-      const int j = i / D, d = i % D;
-      s_k[j * DP + d] = __ldg(kb + (long long)(kt + j) * a.k_stride + d);
-    }
-    __syncthreads();
-    if (live)
-      for (int j = lane; j < nk; j += 32) {
-        const float ds = __ldg(pr + kt + j) * (dp[kt + j] - delta);
+      for (int rr = 0; rr < RW; ++rr) {
+        const float ds = __ldg(a.probs + prow[rr] + kt + j) * (dp0[(size_t)rr * a.Lk + kt + j] - delta[rr]);
 #pragma unroll
-        for (int d = 0; d < D; ++d) dqr[d] = fmaf(ds, s_k[j * DP + d], dqr[d]);
+        for (int d = 0; d < D; ++d) acc[rr * D + d] = fmaf(ds, kk[d], acc[rr * D + d]);
       }
+    }
   }
+  warp_reduce_scatter<N>(acc, lane);
+  constexpr int PER = N >= 32 ? N / 32 : 1;
+  const int e0 = N >= 32 ? lane * PER : lane >> 1;
+  const int r = r0 + e0 / D;
+  if (r < a.Lq && (N >= 32 || (lane & 1) == 0)) {
+    float* o = a.dq + ((long long)b * a.Lq + r) * a.q_stride + h * D + e0 % D;
 #pragma unroll
-  for (int d = 0; d < D; ++d) dqr[d] = warp_sum(dqr[d]) * a.scale;
-  if (live && lane == 0) {
-    float* o = a.dq + ((long long)b * a.Lq + r) * a.q_stride + h * D;
-#pragma unroll
-    for (int d = 0; d < D; ++d) o[d] = a.accum_dq ? o[d] + dqr[d] : dqr[d];
+    for (int i = 0; i < PER; ++i) o[i] = a.accum_dq ? o[i] + acc[i] * a.scale : acc[i] * a.scale;
   }
 }
 
-// per key j (one thread each, 128 keys per CTA): dV[j] = sum_i P[i,j] dO[i],
-// dK[j] = scale * sum_i P[i,j] (dO[i].V[j] - delta[i]) Q[i]; the query rows stream through shared memory.
+// per key j (one thread each, 128 keys per CTA): dV[j] = sum_i Pd[i,j] dO[i],
+// dK[j] = scale * sum_i P[i,j] (dPd[i,j] - delta[i]) Q[i]; the query rows stream through shared memory and the
+// probability column is fetched 8 rows at a time so that 8 coalesced loads are in flight per thread.
 constexpr int kBwdKeys = 128;
 constexpr int kBwdQTile = 32;
 
 template <int D>
 __global__ void __launch_bounds__(kBwdKeys) attn_bwd_kv_kernel(AttnBwdArgs a) {
-  __shared__ float s_q[kBwdQTile][D];
-  __shared__ float s_do[kBwdQTile][D];
+  __shared__ __align__(16) float s_q[kBwdQTile][D];
+  __shared__ __align__(16) float s_do[kBwdQTile][D];
   __shared__ float s_delta[kBwdQTile];
   const int bh = blockIdx.y, h = bh / a.B, b = bh % a.B;
   const int j = blockIdx.x * kBwdKeys + threadIdx.x;
@@ -445,30 +510,49 @@ __global__ void __launch_bounds__(kBwdKeys) attn_bwd_kv_kernel(AttnBwdArgs a) {
   for (int i0 = 0; i0 < a.Lq; i0 += kBwdQTile) {
     const int nq = min(kBwdQTile, a.Lq - i0);
     __syncthreads();
-    for (int t = threadIdx.x; t < nq * D; t += blockDim.x) {
+    for (int t = threadIdx.x; t < kBwdQTile * D; t += blockDim.x) {
       const int i = t / D, d = t % D;
-      s_q[i][d] = __ldg(a.q + ((long long)b * a.Lq + i0 + i) * a.q_stride + h * D + d);
-      s_do[i][d] = __ldg(a.dout + ((long long)b * a.Lq + i0 + i) * a.o_stride + h * D + d);
+      const bool in = i < nq;
+      s_q[i][d] = in ? __ldg(a.q + ((long long)b * a.Lq + i0 + i) * a.q_stride + h * D + d) : 0.f;
+      s_do[i][d] = in ? __ldg(a.dout + ((long long)b * a.Lq + i0 + i) * a.o_stride + h * D + d) : 0.f;
     }
-    if (threadIdx.x < nq) s_delta[threadIdx.x] = __ldg(a.delta + (long long)bh * a.Lq + i0 + threadIdx.x);
+    if (threadIdx.x < kBwdQTile)
+      s_delta[threadIdx.x] = threadIdx.x < nq ? __ldg(a.delta + (long long)bh * a.Lq + i0 + threadIdx.x) : 0.f;
     __syncthreads();
     if (live) {
       const long long pofs = ((long long)bh * a.Lq + i0) * a.Lk + j;
-      const float* pc = a.probs + pofs;
-      const unsigned char* kc = a.keep ? a.keep + pofs : nullptr;
-      for (int i = 0; i < nq; ++i) {
-        const float p = __ldg(pc + (long long)i * a.Lk);
-        const float ks = kc ? (kc[(long long)i * a.Lk] ? a.keep_scale : 0.f) : 1.f;
-        const float pd = p * ks;
-        float dpv = 0.f;
+#pragma unroll 1
+      for (int ib = 0; ib < kBwdQTile; ib += 8) {
+        if (ib >= nq) break;
+        float p[8], ks[8];
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          dpv = fmaf(s_do[i][d], vr[d], dpv);
-          dvr[d] = fmaf(pd, s_do[i][d], dvr[d]);
+        for (int u = 0; u < 8; ++u) {
+          const bool in = ib + u < nq;
+          p[u] = in ? __ldg(a.probs + pofs + (long long)(ib + u) * a.Lk) : 0.f;
+          ks[u] = (a.keep && in) ? (a.keep[pofs + (long long)(ib + u) * a.Lk] ? a.keep_scale : 0.f) : 1.f;
         }
-        const float ds = p * (dpv * ks - s_delta[i]);
 #pragma unroll
-        for (int d = 0; d < D; ++d) dkr[d] = fmaf(ds, s_q[i][d], dkr[d]);
+        for (int u = 0; u < 8; ++u) {
+          const int i = ib + u;
+          float dov[D], qv[D];
+#pragma unroll
+          for (int e = 0; e < D / 4; ++e) {
+            const float4 t = *reinterpret_cast<const float4*>(&s_do[i][4 * e]);
+            dov[4 * e] = t.x; dov[4 * e + 1] = t.y; dov[4 * e + 2] = t.z; dov[4 * e + 3] = t.w;
+            const float4 s = *reinterpret_cast<const float4*>(&s_q[i][4 * e]);
+            qv[4 * e] = s.x; qv[4 * e + 1] = s.y; qv[4 * e + 2] = s.z; qv[4 * e + 3] = s.w;
+          }
+          const float pd = p[u] * ks[u];
+          float dpv = 0.f;
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            dpv = fmaf(dov[d], vr[d], dpv);
+            dvr[d] = fmaf(pd, dov[d], dvr[d]);
+          }
+          const float ds = p[u] * (dpv * ks[u] - s_delta[i]);
+#pragma unroll
+          for (int d = 0; d < D; ++d) dkr[d] = fmaf(ds, qv[d], dkr[d]);
+        }
       }
     }
   }
@@ -496,16 +580,23 @@ static int attn_check(const KtAttnDesc* d) {
   return KT_OK;
 }
 
-template <int D>
-static int attn_fwd_launch(const KtAttnDesc* d, AttnArgs a, cudaStream_t st) {
-  a.rows_per_warp = d->lk <= 512 ? 4 : (d->lk <= 1024 ? 2 : 1);
-  const int QT = 8 * a.rows_per_warp;
-  const size_t smem = ((size_t)QT * d->lk + (size_t)kKeyTile * (D + 1) + (size_t)QT * D) * sizeof(float);
+// rows per warp: RW*D per-lane accumulators (<= 64) and a [8*RW][Lk] fp32 score buffer in shared memory
+static int attn_rows_per_warp(int d_head, int lk) {
+  int rw = d_head <= 16 ? 4 : (d_head == 32 ? 2 : 1);
+  while (rw > 1 && ((size_t)8 * rw * lk + (size_t)kKeyTile * (d_head + 4)) * sizeof(float) > (size_t)kMaxDynSmem) rw >>= 1;
+  return rw;
+}
+
+template <int D, int RW>
+static int attn_fwd_launch(const KtAttnDesc* d, const AttnArgs& a, cudaStream_t st) {
+  constexpr int QT = 8 * RW;
+  const size_t smem = ((size_t)QT * d->lk + (size_t)kKeyTile * (D + 4)) * sizeof(float);
+  KT_REQUIRE(smem <= (size_t)kMaxDynSmem, "attention: shared memory budget exceeded (Lk too long)");
   static std::atomic<bool> attr_set{false};
-  if (!attr_set.exchange(true)) KT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  KT_REQUIRE(smem <= (size_t)kMaxDynSmem, "attention: shared memory budget exceeded");
+  if (!attr_set.exchange(true))
+    KT_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<D, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
   dim3 grid((d->lq + QT - 1) / QT, d->heads * d->batch);
-  attn_fwd_kernel<D><<<grid, 256, smem, st>>>(a);
+  attn_fwd_kernel<D, RW><<<grid, 256, smem, st>>>(a);
   KT_CHECK_CUDA(cudaGetLastError());
   return KT_OK;
 }
@@ -516,24 +607,33 @@ int attention_fwd(const KtAttnDesc* d, const float* q, const float* k, const flo
   if (rc) return rc;
   KT_REQUIRE(q && k && v && out && probs, "attention_fwd: null pointer");
   KT_REQUIRE(!keep || (d->keep_scale >= 1.f), "attention_fwd: keep mask given but keep_scale < 1");
-  AttnArgs a{q, k, v, mask, out, probs, keep, probs_dropped, d->keep_scale, d->batch, d->heads, d->lq, d->lk, d->q_stride, d->k_stride, d->v_stride,
-             d->o_stride, d->mask_b_stride, d->mask_q_stride, d->scale, 4};
-  switch (d->d_head) {
-    case 8: return attn_fwd_launch<8>(d, a, st);
-    case 16: return attn_fwd_launch<16>(d, a, st);
-    case 32: return attn_fwd_launch<32>(d, a, st);
-    default: return attn_fwd_launch<64>(d, a, st);
+  AttnArgs a{q, k, v, mask, out, probs, keep, probs_dropped, d->keep_scale, d->batch, d->heads, d->lq, d->lk,
+             d->q_stride, d->k_stride, d->v_stride, d->o_stride, d->mask_b_stride, d->mask_q_stride, d->scale};
+  const int rw = attn_rows_per_warp(d->d_head, d->lk);
+  switch (d->d_head * 8 + rw) {
+    case 8 * 8 + 4: return attn_fwd_launch<8, 4>(d, a, st);
+    case 8 * 8 + 2: return attn_fwd_launch<8, 2>(d, a, st);
+    case 16 * 8 + 4: return attn_fwd_launch<16, 4>(d, a, st);
+    case 16 * 8 + 2: return attn_fwd_launch<16, 2>(d, a, st);
+    case 32 * 8 + 2: return attn_fwd_launch<32, 2>(d, a, st);
+    case 32 * 8 + 1: return attn_fwd_launch<32, 1>(d, a, st);
+    case 64 * 8 + 1: return attn_fwd_launch<64, 1>(d, a, st);
+    default: break;
   }
+  set_error("attention_fwd: unsupported (d_head=%d, Lk=%d)", d->d_head, d->lk);
+  return KT_ERR_INVALID;
 }
 
-template <int D>
-static int attn_bwd_launch(const KtAttnDesc* d, AttnBwdArgs a, cudaStream_t st) {
-  const size_t smem = ((size_t)2 * kKeyTile * (D + 1) + (size_t)8 * d->lk) * sizeof(float);
+template <int D, int RW>
+static int attn_bwd_launch(const KtAttnDesc* d, const AttnBwdArgs& a, cudaStream_t st) {
+  constexpr int QT = 8 * RW;
+  const size_t smem = ((size_t)QT * d->lk + (size_t)kKeyTile * (D + 4)) * sizeof(float);
+  KT_REQUIRE(smem <= (size_t)kMaxDynSmem, "attention: shared memory budget exceeded (Lk too long)");
   static std::atomic<bool> attr_set{false};
-  if (!attr_set.exchange(true)) KT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
-  KT_REQUIRE(smem <= (size_t)kMaxDynSmem, "attention: shared memory budget exceeded");
-  dim3 gq((d->lq + 7) / 8, d->heads * d->batch);
-  attn_bwd_q_kernel<D><<<gq, 256, smem, st>>>(a);
+  if (!attr_set.exchange(true))
+    KT_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_q_kernel<D, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  dim3 gq((d->lq + QT - 1) / QT, d->heads * d->batch);
+  attn_bwd_q_kernel<D, RW><<<gq, 256, smem, st>>>(a);
   KT_CHECK_CUDA(cudaGetLastError());
   dim3 gk((d->lk + kBwdKeys - 1) / kBwdKeys, d->heads * d->batch);
   attn_bwd_kv_kernel<D><<<gk, kBwdKeys, 0, st>>>(a);
@@ -542,95 +642,138 @@ static int attn_bwd_launch(const KtAttnDesc* d, AttnBwdArgs a, cudaStream_t st) 
 }
 
 int attention_bwd(const KtAttnDesc* d, const float* q, const float* k, const float* v, const float* probs,
-                  const unsigned char* keep,
-                  const float* dout, float* dq, float* dk, float* dv, float* delta, int accum_dq, cudaStream_t st) {
+                  const unsigned char* keep, const float* dout, float* dq, float* dk, float* dv, float* delta,
+                  int accum_dq, cudaStream_t st) {
   int rc = attn_check(d);
   if (rc) return rc;
   KT_REQUIRE(q && k && v && probs && dout && dq && dk && dv && delta, "attention_bwd: null pointer");
-  AttnBwdArgs a{q, k, v, probs, dout, keep, d->keep_scale, dq, dk, dv, delta, d->batch, d->heads, d->lq, d->lk, d->q_stride, d->k_stride,
-                d->v_stride, d->o_stride, d->scale, accum_dq};
-  switch (d->d_head) {
-    case 8: return attn_bwd_launch<8>(d, a, st);
-    case 16: return attn_bwd_launch<16>(d, a, st);
-    case 32: return attn_bwd_launch<32>(d, a, st);
-    default: return attn_bwd_launch<64>(d, a, st);
+  AttnBwdArgs a{q, k, v, probs, dout, keep, d->keep_scale, dq, dk, dv, delta, d->batch, d->heads, d->lq, d->lk,
+                d->q_stride, d->k_stride, d->v_stride, d->o_stride, d->scale, accum_dq};
+  const int rw = attn_rows_per_warp(d->d_head, d->lk);
+  switch (d->d_head * 8 + rw) {
+    case 8 * 8 + 4: return attn_bwd_launch<8, 4>(d, a, st);
+    case 8 * 8 + 2: return attn_bwd_launch<8, 2>(d, a, st);
+    case 16 * 8 + 4: return attn_bwd_launch<16, 4>(d, a, st);
+    case 16 * 8 + 2: return attn_bwd_launch<16, 2>(d, a, st);
+    case 32 * 8 + 2: return attn_bwd_launch<32, 2>(d, a, st);
+    case 32 * 8 + 1: return attn_bwd_launch<32, 1>(d, a, st);
+    case 64 * 8 + 1: return attn_bwd_launch<64, 1>(d, a, st);
+    default: break;
   }
+  set_error("attention_bwd: unsupported (d_head=%d, Lk=%d)", d->d_head, d->lk);
+  return KT_ERR_INVALID;
 }
 
 // ------------------------------------------------------------------------------------------------
 // FSMN memory block (fsmn.py:46-77): depthwise FIR over time with asymmetric zero padding + skip,
 // padded frames zeroed on the way in and on the way out.
 //   xm = x * keep;   y[b,t,c] = keep[b,t] * ( xm[b,t,c] + sum_j w[c][j] * xm[b, t + j - lp, c] )
+// The data gradient is the same filter with the taps reversed (lp -> K-1-lp) applied to dy.
+// CTA = 64 time steps x 64 channels of one batch item: the (64 + K - 1) x 64 input tile (masked rows zeroed)
+// and the [K][64] weight tile sit in shared memory; a thread owns one channel and 16 consecutive time steps
+// and slides a 16-register window over the taps (per tap: 2 LDS + 16 FMA).
 // ------------------------------------------------------------------------------------------------
-__global__ void fsmn_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                const unsigned char* __restrict__ mask, float* __restrict__ y, int B, int T, int C,
-                                int K, int lp) {
-  const long long total = (long long)B * T * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const long long bt = i / C;
-    const int t = (int)(bt % T), b = (int)(bt / T);
-    if (mask && mask[bt]) {
-      y[i] = 0.f;
-      continue;
+constexpr int kFsT = 64, kFsC = 64, kFsTT = 16;
+
+__global__ void __launch_bounds__(256) fsmn_fir_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                       const unsigned char* __restrict__ mask, float* __restrict__ y,
+                                                       int T, int C, int K, int lp, int reverse) {
+  extern __shared__ float sm[];
+  float* s_x = sm;                                  // [kFsT + K - 1][kFsC]
+  float* s_w = sm + (size_t)(kFsT + K - 1) * kFsC;  // [K][kFsC]
+  const int b = blockIdx.z, t0 = blockIdx.x * kFsT, c0 = blockIdx.y * kFsC;
+  const int rows = kFsT + K - 1;
+  for (int i = threadIdx.x; i < rows * kFsC; i += blockDim.x) {
+    const int rr = i / kFsC, cc = i % kFsC;
+    const int t = t0 + rr - lp, c = c0 + cc;
+    float v = 0.f;
+    if (t >= 0 && t < T && c < C && !(mask && mask[(long long)b * T + t])) v = __ldg(x + ((long long)b * T + t) * C + c);
+    s_x[i] = v;
+  }
+  for (int i = threadIdx.x; i < K * kFsC; i += blockDim.x) {
+    const int j = i / kFsC, cc = i % kFsC, c = c0 + cc;
+    s_w[i] = c < C ? __ldg(w + (long long)c * K + (reverse ? K - 1 - j : j)) : 0.f;
+  }
+  __syncthreads();
+  const int cc = threadIdx.x % kFsC, tq = (threadIdx.x / kFsC) * kFsTT;
+  float acc[kFsTT], win[kFsTT];
+#pragma unroll
+  for (int u = 0; u < kFsTT; ++u) {
+    acc[u] = s_x[(tq + u + lp) * kFsC + cc];   // the skip term xm[b,t,c]
+    win[u] = s_x[(tq + u) * kFsC + cc];
+  }
+  for (int j = 0; j < K; ++j) {
+    const float wj = s_w[j * kFsC + cc];
+#pragma unroll
+    for (int u = 0; u < kFsTT; ++u) acc[u] = fmaf(wj, win[u], acc[u]);
+#pragma unroll
+    for (int u = 0; u < kFsTT - 1; ++u) win[u] = win[u + 1];
+    win[kFsTT - 1] = (j + 1 < K) ? s_x[(tq + kFsTT + j) * kFsC + cc] : 0.f;
+  }
+  const int c = c0 + cc;
+  if (c < C) {
+#pragma unroll
+    for (int u = 0; u < kFsTT; ++u) {
+      const int t = t0 + tq + u;
+      if (t < T) y[((long long)b * T + t) * C + c] = (mask && mask[(long long)b * T + t]) ? 0.f : acc[u];
     }
-    float acc = __ldg(x + i);
-    const float* wc = w + (long long)c * K;
-    for (int j = 0; j < K; ++j) {
-      const int s = t + j - lp;
-      if (s < 0 || s >= T) continue;
-      if (mask && mask[(long long)b * T + s]) continue;
-      acc = fmaf(__ldg(wc + j), __ldg(x + ((long long)b * T + s) * C + c), acc);
-    }
-    y[i] = acc;
   }
 }
 
-// dx[b,s,c] = keep[b,s] * ( dym[b,s,c] + sum_j w[c][j] * dym[b, s - j + lp, c] ),  dym = dy * keep
-__global__ void fsmn_bwd_data_kernel(const float* __restrict__ dy, const float* __restrict__ w,
-                                     const unsigned char* __restrict__ mask, float* __restrict__ dx, int B, int T, int C,
-                                     int K, int lp) {
-  const long long total = (long long)B * T * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    const long long bt = i / C;
-    const int s = (int)(bt % T), b = (int)(bt / T);
-    if (mask && mask[bt]) {
-      dx[i] = 0.f;
-      continue;
-    }
-    float acc = __ldg(dy + i);
-    const float* wc = w + (long long)c * K;
-    for (int j = 0; j < K; ++j) {
-      const int t = s - j + lp;
-      if (t < 0 || t >= T) continue;
-      if (mask && mask[(long long)b * T + t]) continue;
-      acc = fmaf(__ldg(wc + j), __ldg(dy + ((long long)b * T + t) * C + c), acc);
-    }
-    dx[i] = acc;
-  }
-}
-
-// dw[c][j] = sum_{b,t} dym[b,t,c] * xm[b, t + j - lp, c].  CTA = 32 channels x 8 warps (taps strided over
-// warps), one (batch item, time chunk) per blockIdx.y; partials [chunks][C*K] reduced by colsum_partials.
+// dw[c][j] = sum_{b,t} dym[b,t,c] * xm[b, t + j - lp, c].  CTA = (batch item, 256-step time chunk, 64 channels);
+// a thread owns one channel and TJ consecutive taps (a sliding TJ-register window over x: per time step 2 LDS +
+// TJ FMA).  Per-CTA partials [chunk][C*K] are reduced by colsum_partials_kernel (deterministic).
 constexpr int kFsmnChunk = 256;
-__global__ void fsmn_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy,
-                                       const unsigned char* __restrict__ mask, float* __restrict__ partial, int B, int T,
-                                       int C, int K, int lp, int chunks_per_b) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
-  const int b = blockIdx.y / chunks_per_b, t0 = (blockIdx.y % chunks_per_b) * kFsmnChunk;
-  const int t1 = min(T, t0 + kFsmnChunk);
-  if (c >= C) return;
-  for (int j = w; j < K; j += 8) {
-    float acc = 0.f;
-    for (int t = t0; t < t1; ++t) {
-      const int s = t + j - lp;
-      if (s < 0 || s >= T) continue;
-      if (mask && (mask[(long long)b * T + t] || mask[(long long)b * T + s])) continue;
-      acc = fmaf(__ldg(dy + ((long long)b * T + t) * C + c), __ldg(x + ((long long)b * T + s) * C + c), acc);
+
+template <int TJ>
+__global__ void __launch_bounds__(256) fsmn_bwd_weight_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                              const unsigned char* __restrict__ mask,
+                                                              float* __restrict__ partial, int T, int C, int K, int lp,
+                                                              int chunks_per_b) {
+  extern __shared__ float sm[];
+  const int rows = kFsT + 4 * TJ - 1;               // taps padded to 4*TJ >= K
+  float* s_x = sm;                                  // [rows][kFsC]
+  float* s_dy = sm + (size_t)rows * kFsC;           // [kFsT][kFsC]
+  const int b = blockIdx.y / chunks_per_b, tc0 = (blockIdx.y % chunks_per_b) * kFsmnChunk;
+  const int c0 = blockIdx.x * kFsC;
+  const int cc = threadIdx.x % kFsC, j0 = (threadIdx.x / kFsC) * TJ;
+  float acc[TJ];
+#pragma unroll
+  for (int u = 0; u < TJ; ++u) acc[u] = 0.f;
+  for (int t0 = tc0; t0 < min(T, tc0 + kFsmnChunk); t0 += kFsT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * kFsC; i += blockDim.x) {
+      const int rr = i / kFsC, ci = i % kFsC;
+      const int t = t0 + rr - lp, c = c0 + ci;
+      float v = 0.f;
+      if (t >= 0 && t < T && c < C && !(mask && mask[(long long)b * T + t])) v = __ldg(x + ((long long)b * T + t) * C + c);
+      s_x[i] = v;
     }
-    partial[(long long)blockIdx.y * C * K + (long long)c * K + j] = acc;
+    for (int i = threadIdx.x; i < kFsT * kFsC; i += blockDim.x) {
+      const int rr = i / kFsC, ci = i % kFsC;
+      const int t = t0 + rr, c = c0 + ci;
+      float v = 0.f;
+      if (t < T && c < C && !(mask && mask[(long long)b * T + t])) v = __ldg(dy + ((long long)b * T + t) * C + c);
+      s_dy[i] = v;
+    }
+    __syncthreads();
+    float win[TJ];
+#pragma unroll
+    for (int u = 0; u < TJ; ++u) win[u] = s_x[(j0 + u) * kFsC + cc];
+    for (int t = 0; t < kFsT; ++t) {
+      const float d = s_dy[t * kFsC + cc];
+#pragma unroll
+      for (int u = 0; u < TJ; ++u) acc[u] = fmaf(d, win[u], acc[u]);
+#pragma unroll
+      for (int u = 0; u < TJ - 1; ++u) win[u] = win[u + 1];
+      win[TJ - 1] = (t + 1 < kFsT) ? s_x[(t + 1 + j0 + TJ - 1) * kFsC + cc] : 0.f;
+    }
+  }
+  const int c = c0 + cc;
+  if (c < C) {
+#pragma unroll
+    for (int u = 0; u < TJ; ++u)
+      if (j0 + u < K) partial[(long long)blockIdx.y * C * K + (long long)c * K + j0 + u] = acc[u];
   }
 }
 
@@ -644,20 +787,43 @@ static int grid_for(long long n, int threads) {
   return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 
+static int fsmn_fir_launch(const float* x, const float* w, const unsigned char* mask, float* y, int B, int T, int C,
+                           int K, int lp, int reverse, cudaStream_t st) {
+  const size_t smem = ((size_t)(kFsT + K - 1) * kFsC + (size_t)K * kFsC) * sizeof(float);
+  KT_REQUIRE(K <= 256 && B <= 65535, "fsmn: need K <= 256, B <= 65535");
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.exchange(true))
+    KT_CHECK_CUDA(cudaFuncSetAttribute(fsmn_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  dim3 grid((T + kFsT - 1) / kFsT, (C + kFsC - 1) / kFsC, B);
+  fsmn_fir_kernel<<<grid, 256, smem, st>>>(x, w, mask, y, T, C, K, lp, reverse);
+  KT_CHECK_CUDA(cudaGetLastError());
+  return KT_OK;
+}
+
 int fsmn_fwd(const float* x, const float* w, const unsigned char* mask, float* y, int B, int T, int C, int K, int lp,
              cudaStream_t st) {
-  KT_REQUIRE(x && w && y && B >= 1 && T >= 1 && C >= 1 && K >= 1 && lp >= 0, "fsmn_fwd: bad arguments");
-  fsmn_fwd_kernel<<<grid_for((long long)B * T * C, 256), 256, 0, st>>>(x, w, mask, y, B, T, C, K, lp);
+  KT_REQUIRE(x && w && y && B >= 1 && T >= 1 && C >= 1 && K >= 1 && lp >= 0 && lp < K, "fsmn_fwd: bad arguments");
+  return fsmn_fir_launch(x, w, mask, y, B, T, C, K, lp, 0, st);
+}
+
+template <int TJ>
+static int fsmn_wgrad_launch(const float* x, const float* dy, const unsigned char* mask, float* ws, int B, int T, int C,
+                             int K, int lp, int cpb, cudaStream_t st) {
+  const size_t smem = ((size_t)(kFsT + 4 * TJ - 1) * kFsC + (size_t)kFsT * kFsC) * sizeof(float);
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.exchange(true))
+    KT_CHECK_CUDA(cudaFuncSetAttribute(fsmn_bwd_weight_kernel<TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+  fsmn_bwd_weight_kernel<TJ><<<dim3((C + kFsC - 1) / kFsC, B * cpb), 256, smem, st>>>(x, dy, mask, ws, T, C, K, lp, cpb);
   KT_CHECK_CUDA(cudaGetLastError());
   return KT_OK;
 }
 
 int fsmn_bwd(const float* x, const float* dy, const float* w, const unsigned char* mask, float* dx, float* dw,
              float* workspace, long long workspace_floats, int B, int T, int C, int K, int lp, cudaStream_t st) {
-  KT_REQUIRE(x && dy && w && B >= 1 && T >= 1 && C >= 1 && K >= 1 && lp >= 0, "fsmn_bwd: bad arguments");
+  KT_REQUIRE(x && dy && w && B >= 1 && T >= 1 && C >= 1 && K >= 1 && lp >= 0 && lp < K, "fsmn_bwd: bad arguments");
   if (dx) {
-    fsmn_bwd_data_kernel<<<grid_for((long long)B * T * C, 256), 256, 0, st>>>(dy, w, mask, dx, B, T, C, K, lp);
-    KT_CHECK_CUDA(cudaGetLastError());
+    int rc = fsmn_fir_launch(dy, w, mask, dx, B, T, C, K, K - 1 - lp, 1, st);
+    if (rc) return rc;
   }
   if (dw) {
     const int cpb = (T + kFsmnChunk - 1) / kFsmnChunk;
@@ -665,9 +831,14 @@ int fsmn_bwd(const float* x, const float* dy, const float* w, const unsigned cha
       set_error("fsmn_bwd: workspace too small");
       return KT_ERR_WORKSPACE;
     }
-    KT_REQUIRE(B * cpb <= 65535, "fsmn_bwd: too many chunks");
-    fsmn_bwd_weight_kernel<<<dim3((C + 31) / 32, B * cpb), 256, 0, st>>>(x, dy, mask, workspace, B, T, C, K, lp, cpb);
-    KT_CHECK_CUDA(cudaGetLastError());
+    KT_REQUIRE(B * cpb <= 65535 && K <= 64, "fsmn_bwd: need B * chunks <= 65535 and K <= 64");
+    const int tj = (K + 3) / 4;
+    int rc;
+    if (tj <= 4) rc = fsmn_wgrad_launch<4>(x, dy, mask, workspace, B, T, C, K, lp, cpb, st);
+    else if (tj <= 8) rc = fsmn_wgrad_launch<8>(x, dy, mask, workspace, B, T, C, K, lp, cpb, st);
+    else if (tj <= 12) rc = fsmn_wgrad_launch<12>(x, dy, mask, workspace, B, T, C, K, lp, cpb, st);
+    else rc = fsmn_wgrad_launch<16>(x, dy, mask, workspace, B, T, C, K, lp, cpb, st);
+    if (rc) return rc;
     colsum_partials_kernel<<<(C * K + 127) / 128, 128, 0, st>>>(workspace, dw, B * cpb, C * K);
     KT_CHECK_CUDA(cudaGetLastError());
   }

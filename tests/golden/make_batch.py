@@ -17,6 +17,8 @@ def make_sambert_batch(cfg, B, L, gen, short=2):
     dur = dur * (torch.arange(L)[None, :] < in_len[:, None])
     # make row 0 the longest and its length a multiple of r
     dur[0, 0] += (-int(dur[0].sum())) % r + r
+    while B > 1 and int(dur[0].sum()) < int(dur[1:].sum(1).max()):
+        dur[0, 0] += r
     out_len = dur.sum(1)
     T = int(out_len.max())
     assert T % r == 0 and int(out_len[0]) == T
