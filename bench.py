@@ -328,11 +328,18 @@ def roofline_leg(step, batch, ops, ms_per_step):
     """One extra instrumented step: every conv library call is bracketed by CUDA events on the
     launching stream; the dominant kernel class's achieved algorithmic rate is reported against the
     measured peak (MEASURED_PEAKS.json, else the B200_PROFILING.md fallback)."""
+    from kantts_b200 import hifigan
     step.invalidate_weight_caches()        # eager launches after graph replays: prepared weights must be rebuilt
-    prof = ops.set_profiler(True)
-    step._eager_step(*batch)
-    summ = prof.summary()
-    ops.set_profiler(False)
+    # side streams OFF for this step: with concurrent streams an event pair around one launch also measures the
+    # time the kernel spent queued behind other streams' kernels, i.e. not that kernel's own duration
+    par, hifigan._PARALLEL_STREAMS = hifigan._PARALLEL_STREAMS, False
+    try:
+        prof = ops.set_profiler(True)
+        step._eager_step(*batch)
+        summ = prof.summary()
+    finally:
+        ops.set_profiler(False)
+        hifigan._PARALLEL_STREAMS = par
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         pk = json.load(open(peaks_path))

@@ -100,6 +100,15 @@ int kt_weight_grad(const float* dw_fwd, const float* v, const float* g, const fl
                    const float* inv_sigma, int32_t mode, int32_t d0, int32_t d1, int32_t k,
                    int32_t transposed, int32_t groups, float* dv, float* dg, void* stream);
 
+/* Same, ACCUMULATING into the parameters' gradient buffers: dv += ..., dg += ..., and (optional, both or
+ * neither) dbias_dst[0..nbias) += dbias_src.  This is torch's AccumulateGrad (`param.grad += grad`, run once
+ * per parameter per backward by the autograd engine under kantts/train/trainer.py:546,580) folded into the
+ * kernel that produces the gradient; the caller zeroes the buffers once per backward. */
+int kt_weight_grad_accum(const float* dw_fwd, const float* v, const float* g, const float* norm,
+                         const float* inv_sigma, int32_t mode, int32_t d0, int32_t d1, int32_t k,
+                         int32_t transposed, int32_t groups, float* dv, float* dg, const float* dbias_src,
+                         float* dbias_dst, int32_t nbias, void* stream);
+
 /* Forward.  x: [B][t_in][nsub][c_in], y: [B][t_out][nsub][c_out]; bias / resid optional (NULL).
  * resid has y's shape and is added AFTER act_out (layers.py:219 `x = xt + x`; hifigan.py:168). */
 int kt_conv1d_fwd(const KtConv1dDesc* d, const float* x, const float* w_fwd, const float* bias,

@@ -49,6 +49,7 @@ _F = ctypes.c_float
 PROTOTYPES = {
     "kt_weight_prepare": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "kt_weight_grad": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "kt_weight_grad_accum": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P],
     "kt_conv1d_fwd": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P],
     "kt_conv1d_bwd_data": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P],
     "kt_conv1d_bwd_weight": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P],

@@ -8,7 +8,8 @@ int conv1d_fwd_ffma(const KtConv1dDesc*, const float*, const float*, const float
 int conv1d_bwd_data_ffma(const KtConv1dDesc*, const float*, const float*, const float*, const float*, float*, cudaStream_t);
 int conv1d_bwd_weight_ffma(const KtConv1dDesc*, const float*, const float*, const float*, float*, float*, cudaStream_t);
 int weight_prepare(const float*, const float*, const float*, int, int, int, int, int, int, float*, float*, float*, float*, cudaStream_t);
-int weight_grad(const float*, const float*, const float*, const float*, const float*, int, int, int, int, int, int, float*, float*, cudaStream_t);
+int weight_grad(const float*, const float*, const float*, const float*, const float*, int, int, int, int, int, int, float*, float*, int,
+                const float*, float*, int, cudaStream_t);
 int sinadd_fwd(const float*, float*, long long, cudaStream_t);
 int sinadd_bwd(const float*, const float*, float*, long long, cudaStream_t);
 int add3_scale(const float*, const float*, const float*, float, float*, long long, cudaStream_t);
@@ -53,7 +54,14 @@ int kt_weight_prepare(const float* v, const float* g, const float* inv_sigma, in
 int kt_weight_grad(const float* dw_fwd, const float* v, const float* g, const float* norm, const float* inv_sigma,
                    int32_t mode, int32_t d0, int32_t d1, int32_t k, int32_t transposed, int32_t groups, float* dv,
                    float* dg, void* stream) {
-  return kt::weight_grad(dw_fwd, v, g, norm, inv_sigma, mode, d0, d1, k, transposed, groups, dv, dg, ST(stream));
+  return kt::weight_grad(dw_fwd, v, g, norm, inv_sigma, mode, d0, d1, k, transposed, groups, dv, dg, 0, nullptr, nullptr, 0, ST(stream));
+}
+
+int kt_weight_grad_accum(const float* dw_fwd, const float* v, const float* g, const float* norm, const float* inv_sigma,
+                         int32_t mode, int32_t d0, int32_t d1, int32_t k, int32_t transposed, int32_t groups, float* dv,
+                         float* dg, const float* dbias_src, float* dbias_dst, int32_t nbias, void* stream) {
+  return kt::weight_grad(dw_fwd, v, g, norm, inv_sigma, mode, d0, d1, k, transposed, groups, dv, dg, 1, dbias_src, dbias_dst, nbias,
+                         ST(stream));
 }
 
 int kt_conv1d_fwd(const KtConv1dDesc* d, const float* x, const float* w_fwd, const float* bias, const float* resid,

@@ -65,10 +65,15 @@ __global__ void weight_prepare_kernel(const float* __restrict__ v, const float* 
 __global__ void weight_grad_kernel(const float* __restrict__ dw, const float* __restrict__ v,
                                    const float* __restrict__ g, const float* __restrict__ norm,
                                    const float* __restrict__ inv_sigma, int mode, WLayout L,
-                                   float* __restrict__ dv, float* __restrict__ dg) {
+                                   float* __restrict__ dv, float* __restrict__ dg, int accumulate,
+                                   const float* __restrict__ dbias_src, float* __restrict__ dbias_dst, int nbias) {
   __shared__ float red[8];
   const int a = blockIdx.x;
   const int n = L.d1 * L.k;
+  if (dbias_dst) {   // bias gradient hand-over (+= into the parameter's .grad when accumulating)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nbias; i += gridDim.x * blockDim.x)
+      dbias_dst[i] = accumulate ? dbias_dst[i] + dbias_src[i] : dbias_src[i];
+  }
   const float* vs = v + (long long)a * n;
   float* dvs = dv + (long long)a * n;
   if (mode == 1) {
@@ -80,19 +85,21 @@ __global__ void weight_grad_kernel(const float* __restrict__ dw, const float* __
     }
     dot = block_sum(dot, red);
     const float nrm = norm[a], ga = g[a];
-    if (threadIdx.x == 0) dg[a] = dot / nrm;
+    if (threadIdx.x == 0) dg[a] = accumulate ? dg[a] + dot / nrm : dot / nrm;
     const float c1 = ga / nrm, c2 = ga * dot / (nrm * nrm * nrm);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       long long i_fwd, i_bwd;
       L.map(a, i / L.k, i % L.k, i_fwd, i_bwd);
-      dvs[i] = c1 * dw[L.transposed ? i_bwd : i_fwd] - c2 * vs[i];
+      const float r = c1 * dw[L.transposed ? i_bwd : i_fwd] - c2 * vs[i];
+      dvs[i] = accumulate ? dvs[i] + r : r;
     }
   } else {
     const float scale = inv_sigma ? *inv_sigma : 1.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       long long i_fwd, i_bwd;
       L.map(a, i / L.k, i % L.k, i_fwd, i_bwd);
-      dvs[i] = dw[L.transposed ? i_bwd : i_fwd] * scale;
+      const float r = dw[L.transposed ? i_bwd : i_fwd] * scale;
+      dvs[i] = accumulate ? dvs[i] + r : r;
     }
   }
 }
@@ -111,12 +118,13 @@ int weight_prepare(const float* v, const float* g, const float* inv_sigma, int m
 }
 
 int weight_grad(const float* dw, const float* v, const float* g, const float* norm, const float* inv_sigma,
-                int mode, int d0, int d1, int k, int transposed, int groups, float* dv, float* dg,
-                cudaStream_t st) {
+                int mode, int d0, int d1, int k, int transposed, int groups, float* dv, float* dg, int accumulate,
+                const float* dbias_src, float* dbias_dst, int nbias, cudaStream_t st) {
   KT_REQUIRE(dw && v && dv && d0 > 0 && d1 > 0 && k > 0 && groups > 0, "weight_grad: bad arguments");
   KT_REQUIRE(mode == 0 || (mode == 1 && g && norm && dg), "weight_grad: mode 1 needs g, norm, dg");
   WLayout L{d0, d1, k, transposed, groups};
-  weight_grad_kernel<<<d0, 256, 0, st>>>(dw, v, g, norm, inv_sigma, mode, L, dv, dg);
+  KT_REQUIRE((dbias_dst == nullptr) == (dbias_src == nullptr) && nbias >= 0, "weight_grad: dbias_src / dbias_dst must come together");
+  weight_grad_kernel<<<d0, 256, 0, st>>>(dw, v, g, norm, inv_sigma, mode, L, dv, dg, accumulate, dbias_src, dbias_dst, nbias);
   KT_CHECK_CUDA(cudaGetLastError());
   return KT_OK;
 }

@@ -40,6 +40,27 @@ def _side_streams(device, n):
     return pool[:n]
 
 
+def join_side_streams(device=None):
+    """Make the current stream wait for everything queued on the side-stream pool.  Needed after a backward
+    whose parameter gradients were accumulated inside the kernels (ops.mark_direct_grad): the autograd engine
+    only joins the streams its own AccumulateGrad nodes ran on."""
+    for (dev_type, dev_index), pool in _STREAMS.items():
+        if device is not None and (dev_type, dev_index) != (device.type, device.index):
+            continue
+        cur = torch.cuda.current_stream(torch.device(dev_type, dev_index))
+        for s in pool:
+            cur.wait_stream(s)
+
+
+def _split_pair(outs, fmaps, nb, detach_b):
+    """Results of one batched call on cat([ya, yb]) -> ((outs_a, fmaps_a), (outs_b, fmaps_b)); slices of the
+    channels-last buffers are contiguous, so downstream fast paths (kt_l1_sum) still apply."""
+    det = (lambda t: t.detach()) if detach_b else (lambda t: t)
+    a = ([o[:nb] for o in outs], [[f[:nb] for f in fm] for fm in fmaps])
+    b = ([det(o[nb:]) for o in outs], [[det(f[nb:]) for f in fm] for fm in fmaps])
+    return a, b
+
+
 def _consume_init_weights_rng(weight):
     """kantts/models/utils.py:7-10 ``init_weights`` runs ``m.weight.data.normal_(0, 0.01)`` AFTER
     weight_norm: it overwrites the derived ``weight`` (recomputed from g, v at the next forward), so
@@ -425,6 +446,16 @@ class MultiPeriodDiscriminator(nn.Module):
         return y_d_rs, fmap_rs
 
 
+    def forward_pair(self, ya, yb, detach_b=False):
+        """== (self(ya), self(yb)), evaluated as ONE batch: every layer is launched once on 2B items instead
+        of twice on B (the trainer always runs the discriminators on a (generated, real) pair:
+        trainer.py:519-531,560-566).  No layer of this discriminator mixes batch items, so the results are
+        identical.  ``detach_b``: the second result is returned detached (the reference's no_grad pass)."""
+        assert ya.shape == yb.shape
+        outs, fmaps = self.forward(torch.cat([ya, yb], 0))
+        return _split_pair(outs, fmaps, ya.shape[0], detach_b)
+
+
 # --------------------------------------------------------------------------------------------
 # MultiScaleDiscriminator (hifigan.py:305-478)
 # --------------------------------------------------------------------------------------------
@@ -538,6 +569,31 @@ class MultiScaleDiscriminator(nn.Module):
 
     def forward(self, y):
         """y: (B, 1, T) -> (list of (B, n_i), list of list of (B, C, T_l) feature maps)"""
+        return self._run(y, None)
+
+    def forward_pair(self, ya, yb, detach_b=False):
+        """== (self(ya), self(yb)) evaluated as one batch of 2B (see MultiPeriodDiscriminator.forward_pair).
+        A spectral-normed scale (follow_official_norm: scale 0) updates its power-iteration vectors on every
+        training-mode forward (torch.nn.utils.spectral_norm hook), so its two calls use different sigmas: that
+        scale alone still runs twice, on the two halves of the batch, in the reference's order."""
+        assert ya.shape == yb.shape
+        nb = ya.shape[0]
+        outs, fmaps = self._run(torch.cat([ya, yb], 0), nb)
+        det = (lambda t: t.detach()) if detach_b else (lambda t: t)
+        ra, rb = ([], []), ([], [])
+        for o, fm in zip(outs, fmaps):
+            if isinstance(o, tuple):                       # a scale that ran per half
+                (oa, ob), (fa, fb) = o, fm
+                fb = [det(f) for f in fb]
+                ob = det(ob)
+            else:
+                oa, ob = o[:nb], det(o[nb:])
+                fa, fb = [f[:nb] for f in fm], [det(f[nb:]) for f in fm]
+            ra[0].append(oa); ra[1].append(fa)
+            rb[0].append(ob); rb[1].append(fb)
+        return ra, rb
+
+    def _run(self, y, pair_nb):
         y_d_rs, fmap_rs = [], []
         rows = y.transpose(1, 2).contiguous()                                 # (B, T, 1)
         inputs = [rows]
@@ -549,13 +605,21 @@ class MultiScaleDiscriminator(nn.Module):
         if par:                                                               # the scales themselves are independent
             cur = torch.cuda.current_stream()
             streams = _side_streams(y.device, len(self.discriminators))
+
+        def run_scale(d, x):
+            if pair_nb is not None and any(getattr(l[0], "norm", "") == "spectral" for l in d.convs):
+                oa, fa = d.forward_rows(x[:pair_nb])
+                ob, fb = d.forward_rows(x[pair_nb:])
+                return (oa, ob), (fa, fb)
+            return d.forward_rows(x)
+
         for i, d in enumerate(self.discriminators):
             if par:
                 streams[i].wait_stream(cur)
                 with torch.cuda.stream(streams[i]):
-                    y_d_r, fmap_r = d.forward_rows(inputs[i])
+                    y_d_r, fmap_r = run_scale(d, inputs[i])
             else:
-                y_d_r, fmap_r = d.forward_rows(inputs[i])
+                y_d_r, fmap_r = run_scale(d, inputs[i])
             y_d_rs.append(y_d_r)
             fmap_rs.append(fmap_r)
         if par:

@@ -221,6 +221,42 @@ def prepare_weight(cache, spec, v, g):
     return cache
 
 
+_grad_items = None
+
+
+class grad_items:
+    """Inside this context every op built by this module propagates gradient only for the FIRST ``n`` batch
+    items: the caller guarantees that nothing differentiable hangs off the outputs of the remaining items
+    (train.GanStep batches the generated and the real waveforms through the discriminators in one call; the
+    real half is the reference's ``torch.no_grad()`` pass, trainer.py:527-531).  Backward then runs the data- /
+    weight-gradient kernels on ``n`` items and leaves the rest of every input gradient unwritten."""
+
+    def __init__(self, n):
+        self.n = n
+
+    def __enter__(self):
+        global _grad_items
+        self.prev, _grad_items = _grad_items, self.n
+        return self
+
+    def __exit__(self, *exc):
+        global _grad_items
+        _grad_items = self.prev
+        return False
+
+
+def mark_direct_grad(param, flag=True):
+    """``param.grad`` is a persistent, pre-zeroed buffer (train.FlatGrads): ConvFn.backward accumulates into it
+    inside the gradient kernel (kt_weight_grad_accum) and hands autograd no gradient for it, which removes the
+    engine's one ``grad += new`` launch per parameter per backward.  Unmarked parameters (DistributedDataParallel,
+    plain ``loss.backward()`` users) receive their gradients through autograd as usual."""
+    param._kt_direct = bool(flag)
+
+
+def _is_direct(p):
+    return p is None or (getattr(p, "_kt_direct", False) and p.grad is not None and p.grad.is_contiguous())
+
+
 _FORCE_FFMA = os.environ.get("KANTTS_B200_PATH", "").lower() == "ffma"
 _tc_launches = 0
 
@@ -295,12 +331,15 @@ class ConvFn(torch.autograd.Function):
                 check(lib.kt_conv1d_fwd(ctypes.byref(d), ptr(x), ptr(pw.w_fwd), ptr(bd), ptr(resid), ptr(y),
                                         stream_ptr()), "kt_conv1d_fwd")
         _count(spec.stride if spec.transposed else 1)
-        ctx.spec, ctx.d = spec, d
+        nb = B if _grad_items is None else min(_grad_items, B)     # batch items that carry gradient
+        db = d if nb == B else spec.desc(nb, nsub, t_in)
+        ctx.spec, ctx.d, ctx.nb = spec, db, nb
         ctx.w_bwd, ctx.norm = pw.w_bwd, pw.norm
-        nt_b = _tc_tile(lib, spec, d, 1) if x.requires_grad else 0
+        nt_b = _tc_tile(lib, spec, db, 1) if x.requires_grad else 0
         ctx.nt_bwd = nt_b
-        ctx.img_bwd = pw.tc_image(spec, d, 1, nt_b) if nt_b else None
+        ctx.img_bwd = pw.tc_image(spec, db, 1, nt_b) if nt_b else None
         ctx.has_resid, ctx.has_bias, ctx.has_g = resid is not None, bias is not None, g is not None
+        ctx.params = (v, g, bias)
         ctx.save_for_backward(x, y if spec.act_out != KT_ACT_NONE else None, v, g)
         return y
 
@@ -312,50 +351,68 @@ class ConvFn(torch.autograd.Function):
         dy = dy.contiguous()
         st = stream_ptr()
         dx = dres = dbias = dv = dg = None
+        dy_full = dy
+        if ctx.nb < x.shape[0]:          # grad_items: only the leading items carry gradient (contiguous slices)
+            x_, dy = x[:ctx.nb], dy[:ctx.nb]
+            y_ = None if y is None else y[:ctx.nb]
+        else:
+            x_, y_ = x, y
         if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            pass  # (algorithmic work is computed lazily by _timed when the profiler is on)
+            dx = torch.empty_like(x)     # items >= nb stay unwritten: nothing differentiable consumes them
             if ctx.nt_bwd:
                 global _tc_launches
                 with _timed("conv_dgrad_tc", spec, d):
-                    check(lib.kt_conv1d_bwd_data_tc(ctypes.byref(d), ptr(dy), ptr(y), ptr(ctx.img_bwd), ptr(x),
+                    check(lib.kt_conv1d_bwd_data_tc(ctypes.byref(d), ptr(dy), ptr(y_), ptr(ctx.img_bwd), ptr(x_),
                                                     ptr(dx), st), "kt_conv1d_bwd_data_tc")
                 _tc_launches += 1
             else:
                 with _timed("conv_dgrad_ffma", spec, d):
-                    check(lib.kt_conv1d_bwd_data(ctypes.byref(d), ptr(dy), ptr(y), ptr(ctx.w_bwd), ptr(x), ptr(dx),
+                    check(lib.kt_conv1d_bwd_data(ctypes.byref(d), ptr(dy), ptr(y_), ptr(ctx.w_bwd), ptr(x_), ptr(dx),
                                                  st), "kt_conv1d_bwd_data")
             _count(max(spec.stride if not spec.transposed else 1, spec.upsample))
         if ctx.has_resid and ctx.needs_input_grad[1]:
-            dres = dy
+            dres = dy_full
         need_w = ctx.needs_input_grad[3] or (ctx.has_g and ctx.needs_input_grad[4])
         need_b = ctx.has_bias and ctx.needs_input_grad[2]
         if need_w or need_b:
             dw = torch.empty(spec.w_numel, device=x.device, dtype=torch.float32)
             if need_b:
                 dbias = torch.empty(spec.c_out, device=x.device, dtype=torch.float32)
-            pass  # (algorithmic work is computed lazily by _timed when the profiler is on)
             ws_floats = _wgrad_tc_workspace(lib, spec, d)
             if ws_floats:
                 ws = torch.empty(ws_floats, device=x.device, dtype=torch.float32)
                 with _timed("conv_wgrad_tc", spec, d):
-                    check(lib.kt_conv1d_bwd_weight_tc(ctypes.byref(d), ptr(x), ptr(dy), ptr(y), ptr(dw), ptr(dbias),
+                    check(lib.kt_conv1d_bwd_weight_tc(ctypes.byref(d), ptr(x_), ptr(dy), ptr(y_), ptr(dw), ptr(dbias),
                                                       ptr(ws), ws_floats, st), "kt_conv1d_bwd_weight_tc")
                 _tc_launches += 1
             else:
                 with _timed("conv_wgrad_ffma", spec, d):
-                    check(lib.kt_conv1d_bwd_weight(ctypes.byref(d), ptr(x), ptr(dy), ptr(y), ptr(dw), ptr(dbias), st),
+                    check(lib.kt_conv1d_bwd_weight(ctypes.byref(d), ptr(x_), ptr(dy), ptr(y_), ptr(dw), ptr(dbias), st),
                           "kt_conv1d_bwd_weight")
             _count(4 if need_b else 2)
             if need_w:
+                pv, pg, pb = ctx.params
                 vd = v.detach().contiguous()
-                dv = torch.empty_like(vd)
-                if ctx.has_g:
-                    dg = torch.empty_like(g)
-                check(lib.kt_weight_grad(ptr(dw), ptr(vd), ptr(None if g is None else g.detach().contiguous()),
-                                         ptr(ctx.norm), None, 1 if ctx.has_g else 0, vd.shape[0], vd.shape[1],
-                                         spec.kernel, int(spec.transposed), spec.groups, ptr(dv), ptr(dg), st),
-                      "kt_weight_grad")
+                gd = None if g is None else g.detach().contiguous()
+                mode = 1 if ctx.has_g else 0
+                direct = (pv.is_leaf and _is_direct(pv) and _is_direct(pg) and (not need_b or _is_direct(pb))
+                          and ctx.needs_input_grad[3] and (not ctx.has_g or ctx.needs_input_grad[4]))
+                if direct:
+                    # AccumulateGrad folded into the kernel: param.grad += (train.FlatGrads buffers, pre-zeroed)
+                    check(lib.kt_weight_grad_accum(ptr(dw), ptr(vd), ptr(gd), ptr(ctx.norm), None, mode, vd.shape[0],
+                                                   vd.shape[1], spec.kernel, int(spec.transposed), spec.groups,
+                                                   ptr(pv.grad), None if pg is None else ptr(pg.grad),
+                                                   ptr(dbias) if need_b else None,
+                                                   ptr(pb.grad) if need_b else None, spec.c_out if need_b else 0, st),
+                          "kt_weight_grad_accum")
+                    dbias = None
+                else:
+                    dv = torch.empty_like(vd)
+                    if ctx.has_g:
+                        dg = torch.empty_like(g)
+                    check(lib.kt_weight_grad(ptr(dw), ptr(vd), ptr(gd), ptr(ctx.norm), None, mode, vd.shape[0],
+                                             vd.shape[1], spec.kernel, int(spec.transposed), spec.groups, ptr(dv),
+                                             ptr(dg), st), "kt_weight_grad")
                 _count()
         return dx, dres, dbias, dv, dg, None, None
 

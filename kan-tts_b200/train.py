@@ -22,11 +22,13 @@ exchange is ONE in-place NCCL all-reduce per model per phase with no packing cop
 import torch
 import torch.distributed as dist
 
+from . import ops
+
 
 class FlatGrads:
     """Owns a flat fp32 gradient buffer for a module; every parameter's ``.grad`` is a view."""
 
-    def __init__(self, module):
+    def __init__(self, module, direct=True):
         self.params = [p for p in module.parameters() if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
@@ -35,6 +37,8 @@ class FlatGrads:
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
+            if direct:      # the conv backward kernels accumulate straight into these views (ops.mark_direct_grad)
+                ops.mark_direct_grad(p)
 
     def zero(self):
         self.flat.zero_()
@@ -54,10 +58,12 @@ class GanStep:
     shape and ``criterion`` as built by the reference's builders (or this package's)."""
 
     def __init__(self, model, optimizer, scheduler, criterion, config, skip_unused_d_grads=True, cuda_graph=False,
-                 graph_warmup=3):
+                 graph_warmup=3, pair_discriminators=True):
         self.model, self.optimizer, self.scheduler = model, optimizer, scheduler
         self.criterion, self.config = criterion, config
         self.skip_unused_d_grads = skip_unused_d_grads
+        # run each discriminator ONCE per phase on the (generated, real) pair as a batch of 2B (forward_pair)
+        self.pair_discriminators = pair_discriminators
         self.g_grads = FlatGrads(model["generator"])
         self.d_grads = {k: FlatGrads(m) for k, m in model["discriminator"].items()}
         self.steps = 1
@@ -94,18 +100,28 @@ class GanStep:
                     fg.set_requires_grad(False)
             adv_loss = 0.0
             fmap_lst_ = []
+            want_fm = bool(crit.get("feat_match_loss", None))
+            paired = self._can_pair() and want_fm
+            fmap_lst = []
             for name, disc in model["discriminator"].items():
-                p_, fmap_ = disc(y_)
+                if paired:
+                    # disc(y_) [with grad] and the no_grad disc(y) of trainer.py:527-531 as one batch: only the
+                    # first B items (y_) carry gradient, the real half is returned detached
+                    with ops.grad_items(y_.shape[0]):
+                        (p_, fmap_), (_, fmap) = disc.forward_pair(y_, y, detach_b=True)
+                    fmap_lst.append(fmap)
+                else:
+                    p_, fmap_ = disc(y_)
                 fmap_lst_.append(fmap_)
                 adv_loss = adv_loss + crit["generator_adv_loss"](p_)
             gen_loss = gen_loss + adv_loss * crit["generator_adv_loss"].weights
             log["adversarial_loss"] = adv_loss
-            if crit.get("feat_match_loss", None):
-                fmap_lst = []
-                for name, disc in model["discriminator"].items():
-                    with torch.no_grad():
-                        p, fmap = disc(y)
-                        fmap_lst.append(fmap)
+            if want_fm:
+                if not paired:
+                    for name, disc in model["discriminator"].items():
+                        with torch.no_grad():
+                            p, fmap = disc(y)
+                            fmap_lst.append(fmap)
                 fm_loss = 0.0
                 for fmap_, fmap in zip(fmap_lst, fmap_lst_):          # argument order: trainer.py:535-538
                     fm_loss = fm_loss + crit["feat_match_loss"](fmap_, fmap)
@@ -117,6 +133,7 @@ class GanStep:
         log["generator_loss"] = gen_loss
         self.g_grads.zero()
         gen_loss.backward()
+        self._join_streams(y)
 
     def _seg_gopt_discriminator(self, y, x):
         """generator Adam (trainer.py:547-553), then discriminator forward/backward (:556-580)"""
@@ -132,8 +149,11 @@ class GanStep:
             dis_loss = 0.0
             real_t, fake_t = 0.0, 0.0
             for name, disc in model["discriminator"].items():
-                p, fmap = disc(y)
-                p_, fmap_ = disc(y_.detach())
+                if self._can_pair():
+                    (p, fmap), (p_, fmap_) = disc.forward_pair(y, y_.detach())     # trainer.py:560-561 as one batch
+                else:
+                    p, fmap = disc(y)
+                    p_, fmap_ = disc(y_.detach())
                 real_loss, fake_loss = crit["discriminator_adv_loss"](p_, p)
                 dis_loss = dis_loss + real_loss + fake_loss
                 real_t, fake_t = real_t + real_loss, fake_t + fake_loss
@@ -141,6 +161,18 @@ class GanStep:
             for fg in self.d_grads.values():
                 fg.zero()
             dis_loss.backward()
+            self._join_streams(y)
+
+    def _can_pair(self):
+        return self.pair_discriminators and all(hasattr(d, "forward_pair") for d in self.model["discriminator"].values())
+
+    @staticmethod
+    def _join_streams(t):
+        # parameter gradients accumulated inside the kernels (FlatGrads -> ops.mark_direct_grad) may still be in
+        # flight on the side streams of the parallel sub-discriminators / resblocks
+        if t.is_cuda:
+            from . import hifigan
+            hifigan.join_side_streams(t.device)
 
     def _seg_dopt(self):
         """discriminator Adam (trainer.py:581-589)"""

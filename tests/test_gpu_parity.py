@@ -244,9 +244,11 @@ def _small_config(g):
             "generator_grad_norm": -1, "discriminator_grad_norm": -1}
 
 
+@pytest.mark.parametrize("pair", [True, False])
 @pytest.mark.parametrize("force_ffma", [True, False])
-def test_gan_train_step_matches_reference_trainer(golden, force_ffma):
-    """One full GAN step (both phases, Adam) vs the unmodified GAN_Trainer.train_step."""
+def test_gan_train_step_matches_reference_trainer(golden, force_ffma, pair):
+    """One full GAN step (both phases, Adam) vs the unmodified GAN_Trainer.train_step.  ``pair``: the
+    discriminators run once per phase on the (generated, real) pair as one batch (GanStep default)."""
     g = golden("trainstep_small")
     cfg = _small_config(g)
     ops.set_force_ffma(force_ffma)
@@ -257,7 +259,7 @@ def test_gan_train_step_matches_reference_trainer(golden, force_ffma):
         model["discriminator"]["MultiScaleDiscriminator"].load_state_dict(g.group("before/msd/"))
         model["discriminator"]["MultiPeriodDiscriminator"].load_state_dict(g.group("before/mpd/"))
         crit = K.criterion_builder(cfg, DEV)
-        step = K.GanStep(model, opt, sched, crit, cfg)
+        step = K.GanStep(model, opt, sched, crit, cfg, pair_discriminators=pair)
         log = K.train.losses_to_float(step.step((g.t("y").to(DEV), g.t("x").to(DEV))))
     finally:
         ops.set_force_ffma(False)
@@ -273,6 +275,60 @@ def test_gan_train_step_matches_reference_trainer(golden, force_ffma):
             num += float(((sd[k].cpu() - v).double() ** 2).sum())
             den += float(((before[k] - v).double() ** 2).sum())
         assert num <= 2e-2 * den, (tag, num, den)      # Adam's first step is lr*sign-like: loose on purpose
+
+
+@pytest.mark.parametrize("name,cls", [("mpd_small", "MultiPeriodDiscriminator"), ("msd_small", "MultiScaleDiscriminator")])
+def test_forward_pair_equals_two_calls(golden, name, cls):
+    """forward_pair(ya, yb) == (d(ya), d(yb)) incl. the spectral-norm power-iteration state, and with
+    ops.grad_items the input gradient of the first half equals the un-batched one."""
+    g = golden(name)
+    torch.manual_seed(5)
+    T = g.t("y").shape[-1]
+    ya = (0.3 * torch.randn(3, 1, T)).to(DEV).requires_grad_(True)
+    yb = (0.3 * torch.randn(3, 1, T)).to(DEV)
+    res = {}
+    for mode in ("two", "pair"):
+        d = getattr(K, cls)(**g.cfg).to(DEV)
+        d.load_state_dict(g.group("sd/"))
+        d.train()
+        ya.grad = None
+        if mode == "two":
+            oa, fa = d(ya)
+            with torch.no_grad():
+                ob, fb = d(yb)
+        else:
+            with ops.grad_items(3):
+                (oa, fa), (ob, fb) = d.forward_pair(ya, yb, detach_b=True)
+            assert not any(o.requires_grad for o in ob)
+        sum((o * o).sum() for o in oa).backward()
+        res[mode] = ([o.detach().clone() for o in oa], [o.detach().clone() for o in ob],
+                     [f.detach().clone() for fm in fa for f in fm], [f.detach().clone() for fm in fb for f in fm],
+                     ya.grad.clone(), {k: v.clone() for k, v in d.state_dict().items() if k.endswith(("weight_u", "weight_v"))})
+    for i in range(4):
+        for a, b in zip(res["two"][i], res["pair"][i]):
+            assert a.shape == b.shape and rel_l2(b, a) < 1e-4, (i, rel_l2(b, a))
+    assert rel_l2(res["pair"][4], res["two"][4]) < 1e-4
+    for k, v in res["two"][5].items():
+        assert rel_l2(res["pair"][5][k], v) < 1e-5, k
+
+
+def test_direct_grad_accumulation_matches_autograd(golden):
+    """FlatGrads marks parameters for in-kernel accumulation (kt_weight_grad_accum): two backward passes must
+    leave the same .grad as autograd's AccumulateGrad path."""
+    g = golden("gen_small_causal")
+    x = g.t("x").to(DEV)
+    grads = {}
+    for direct in (False, True):
+        m = K.Generator(**g.cfg).to(DEV)
+        m.load_state_dict(g.group("sd/"))
+        fg = K.train.FlatGrads(m, direct=direct)
+        fg.zero()
+        for scale in (1.0, -0.5):
+            (m(x * scale) ** 2).sum().backward()
+        K.hifigan.join_side_streams(x.device)
+        torch.cuda.synchronize()
+        grads[direct] = fg.flat.clone()
+    assert rel_l2(grads[True], grads[False]) < 1e-5, rel_l2(grads[True], grads[False])
 
 
 def test_c1_full_generator_matches_reference(golden):
