@@ -194,7 +194,11 @@ def main():
     ap.add_argument("--cpu-sample-batch", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="EXPERIMENTAL: replay the step as 3 CUDA graphs (crashes on the full-size model in round 1)")
+    ap.add_argument("--launch", default="auto", choices=["auto", "graph", "eager"],
+                    help="graph: replay the step as 2 CUDA graphs; eager: per-kernel launches from Python; auto (default): "
+                         "graph if a capture+replay self-test in a child process succeeds, else eager")
+    ap.add_argument("--graph", action="store_true", help="same as --launch graph")
+    ap.add_argument("--graph-selftest", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--ncu", action="store_true", help="profiling mode: 1 warm-up + K steps, nothing else (not a bench number)")
     args = ap.parse_args()
 
@@ -214,14 +218,37 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.graph_selftest:
+        return graph_selftest(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     W = max(3, args.warmup)
 
+    launch = "graph" if args.graph else args.launch
+    launch_note = ""
+    if args.ncu:
+        launch = "eager"
+    if launch == "auto":
+        # CUDA-graph replay of the full-size step crashed inside cudaGraphLaunch in earlier builds of this round:
+        # prove capture + replay in a CHILD process on this device first, fall back to eager launches otherwise
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT")}
+        env["LOCAL_RANK"] = str(local_rank)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--graph-selftest"], env=env, capture_output=True,
+                               text=True, timeout=300)
+            ok = r.returncode == 0 and "GRAPH_SELFTEST_OK" in r.stdout
+        except Exception:
+            ok = False
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        launch = "graph" if int(flag) == 1 else "eager"
+        launch_note = " (auto: graph self-test %s)" % ("passed" if launch == "graph" else "FAILED -> eager fallback")
+
     torch.manual_seed(1234)                      # identical replicas on every rank (reference RNG stream)
-    use_graph = args.graph and not args.ncu
-    model, opt, sched = K.hifigan_model_builder(CONFIG, dev, capturable=use_graph)
+    use_graph = launch == "graph"
+    model, opt, sched = K.hifigan_model_builder(CONFIG, dev)
     crit = K.criterion_builder(CONFIG, dev)
     step = K.GanStep(model, opt, sched, crit, CONFIG, cuda_graph=use_graph)
     y_h, x_h = synth_batch(B_PER_GPU, 1234 + rank)
@@ -301,7 +328,8 @@ def main():
         "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * world, "segment": T_WAV, "parallelism": f"dp{world}",
                    "precision": "fp32 storage; tcgen05 layers bf16x3 split (fp32-equivalent), others exact fp32 FFMA",
                    "l2": "explicit 256 MB flush write between timed iterations",
-                   "launch": "3 CUDA graphs per step (replay)" if use_graph else "eager launches; independent sub-discriminators / parallel resblocks on side streams",
+                   "launch": ("2 CUDA graphs per step (replay) + eager Adam / NCCL between them" if use_graph else
+                              "eager launches; independent sub-discriminators / parallel resblocks on side streams") + launch_note,
                    "gflop_per_step_as_reference_executes": FLOP_PER_SAMPLE * B_PER_GPU * T_WAV / 1e9},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": (y_h.numel() + x_h.numel()) * 4,
                 "d2h_bytes_per_step": 8},
@@ -322,6 +350,24 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def graph_selftest(dev):
+    """Child-process check: eager warm-up, capture, a few replays, finite losses."""
+    import kantts_b200 as K
+    torch.manual_seed(1234)
+    model, opt, sched = K.hifigan_model_builder(CONFIG, dev)
+    crit = K.criterion_builder(CONFIG, dev)
+    step = K.GanStep(model, opt, sched, crit, CONFIG, cuda_graph=True)
+    y, x = synth_batch(B_PER_GPU, 1234)
+    y, x = y.to(dev), x.to(dev)
+    log = None
+    for _ in range(step.graph_warmup + 4):
+        log = step.step((y, x))
+    torch.cuda.synchronize()
+    vals = [float(v) for v in log.values() if torch.is_tensor(v)]
+    assert step._graphs is not None and all(v == v and abs(v) < 1e6 for v in vals), vals
+    print("GRAPH_SELFTEST_OK", vals, flush=True)
 
 
 def roofline_leg(step, batch, ops, ms_per_step):

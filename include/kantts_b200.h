@@ -154,6 +154,13 @@ int kt_sinadd_bwd(const float* x, const float* dy, float* dx, int64_t n, void* s
 /* y = scale * (a + b + c)   (hifigan.py:170-176: mean over the resblocks; b, c optional) */
 int kt_add3_scale(const float* a, const float* b, const float* c, float scale, float* y, int64_t n, void* stream);
 
+/* Second half of the data gradient of the nearest-upsampled conv (hifigan.py:82-97, `repeat_upsamples`):
+ * dx[r][c] = act_in'(x[r][c]) * sum_{u<up} dxu[r*up + u][c], where dxu is the data gradient of the SAME conv
+ * taken with upsample = 1 / act_in = NONE over t_in*up input rows (kt_conv1d_bwd_data[_tc]).  rows = B*t_in,
+ * c % 4 == 0; x may be NULL when act_in == KT_ACT_NONE. */
+int kt_upsample_grad_reduce(const float* dxu, const float* x, int32_t act_in, float act_in_slope, float* dx,
+                            int64_t rows, int32_t up, int32_t c, void* stream);
+
 /* db3 single-level analysis DWT, zero padding (pytorch_wavelets.DWT1DForward as used at
  * hifigan.py:445-448,469-471) fused with torch.cat([yl, yh], dim=1): x [B][T] -> y [B][T2][2]
  * with T2 = (T + 5) / 2, channel 0 = low-pass, 1 = high-pass. */

@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkantts_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "conv_ffma.cu", "conv_tc.cu", "wgrad_tc.cu", "weights.cu", "misc.cu", "stft_mel.cu", "sambert.cu"]
+SOURCES = ["api.cu", "conv_ffma.cu", "conv_tc.cu", "wgrad_tc.cu", "weights.cu", "misc.cu", "stft_mel.cu", "sambert.cu", "thin.cu"]
 
 KT_ACT_NONE, KT_ACT_LRELU, KT_ACT_TANH = 0, 1, 2
 KT_PATH_AUTO, KT_PATH_FFMA, KT_PATH_TC = 0, 1, 2
@@ -56,6 +56,7 @@ PROTOTYPES = {
     "kt_sinadd_fwd": [_P, _P, _L, _P],
     "kt_sinadd_bwd": [_P, _P, _P, _L, _P],
     "kt_add3_scale": [_P, _P, _P, _F, _P, _L, _P],
+    "kt_upsample_grad_reduce": [_P, _P, _I, _F, _P, _L, _I, _I, _P],
     "kt_dwt_db3_fwd": [_P, _P, _I, _I, _P],
     "kt_dwt_db3_bwd": [_P, _P, _I, _I, _P],
     "kt_stft_mel_fwd": [ctypes.POINTER(KtMelDesc), _P, _P, _P, _P, _P, _P, _P],

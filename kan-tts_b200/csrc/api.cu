@@ -13,6 +13,7 @@ int weight_grad(const float*, const float*, const float*, const float*, const fl
 int sinadd_fwd(const float*, float*, long long, cudaStream_t);
 int sinadd_bwd(const float*, const float*, float*, long long, cudaStream_t);
 int add3_scale(const float*, const float*, const float*, float, float*, long long, cudaStream_t);
+int upsample_grad_reduce(const float*, const float*, int, float, float*, long long, int, int, cudaStream_t);
 int dwt_fwd(const float*, float*, int, int, cudaStream_t);
 int dwt_bwd(const float*, float*, int, int, cudaStream_t);
 int l1_sum(const float*, const float*, long long, float, float*, cudaStream_t);
@@ -95,6 +96,10 @@ int kt_sinadd_fwd(const float* x, float* y, int64_t n, void* stream) { return kt
 int kt_sinadd_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream) { return kt::sinadd_bwd(x, dy, dx, n, ST(stream)); }
 int kt_add3_scale(const float* a, const float* b, const float* c, float scale, float* y, int64_t n, void* stream) {
   return kt::add3_scale(a, b, c, scale, y, n, ST(stream));
+}
+int kt_upsample_grad_reduce(const float* dxu, const float* x, int32_t act_in, float act_in_slope, float* dx, int64_t rows,
+                            int32_t up, int32_t c, void* stream) {
+  return kt::upsample_grad_reduce(dxu, x, act_in, act_in_slope, dx, rows, up, c, ST(stream));
 }
 int kt_dwt_db3_fwd(const float* x, float* y, int32_t batch, int32_t t, void* stream) { return kt::dwt_fwd(x, y, batch, t, ST(stream)); }
 int kt_dwt_db3_bwd(const float* dy, float* dx, int32_t batch, int32_t t, void* stream) { return kt::dwt_bwd(dy, dx, batch, t, ST(stream)); }

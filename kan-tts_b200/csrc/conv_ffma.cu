@@ -617,8 +617,13 @@ std::vector<Phase> conv_phases(const KtConv1dDesc* d, int dir) {
   return v;
 }
 
+bool thin_cin1_ok(const KtConv1dDesc* d);                                                                       // thin.cu
+int thin_cin1_fwd(const KtConv1dDesc*, const float*, const float*, const float*, float*, cudaStream_t);
+int thin_cin1_wgrad(const KtConv1dDesc*, const float*, const float*, const float*, float*, float*, cudaStream_t);
+
 int conv1d_fwd_ffma(const KtConv1dDesc* d, const float* x, const float* w_fwd, const float* bias,
                     const float* resid, float* y, cudaStream_t st) {
+  if (thin_cin1_ok(d) && resid == nullptr) return thin_cin1_fwd(d, x, w_fwd, bias, y, st);   // waveform-input layers
   CoreParams p{};
   p.in = make_side(x, nullptr, d->act_in, d->act_in_slope, false);
   p.w = w_fwd; p.bias = bias; p.resid = resid; p.mask = Side{nullptr, nullptr, 0, 0.f}; p.out = y;
@@ -657,6 +662,7 @@ int conv1d_bwd_data_ffma(const KtConv1dDesc* d, const float* dy, const float* y,
 int conv1d_bwd_weight_ffma(const KtConv1dDesc* d, const float* x, const float* dy, const float* y,
                            float* dw, float* dbias, cudaStream_t st) {
   KT_REQUIRE(d->act_out == KT_ACT_NONE || y != nullptr, "bwd_weight: y required when act_out != NONE");
+  if (thin_cin1_ok(d)) return thin_cin1_wgrad(d, x, dy, y, dw, dbias, st);
   const size_t wn = (size_t)d->kernel * (d->c_in / d->groups) * d->c_out;
   KT_CHECK_CUDA(cudaMemsetAsync(dw, 0, wn * sizeof(float), st));
   const Side sx = make_side(x, nullptr, d->act_in, d->act_in_slope, false);

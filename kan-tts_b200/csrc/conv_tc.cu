@@ -44,8 +44,14 @@ constexpr int kTcMaxGroups = 8;  // residue classes (= input step) per phase
 // (C_in = 1, 32, 80, ...), single-output and GROUPED layers use the same kernel: tile nt covers the
 // columns [nt * n_stride, nt * n_stride + min(n_stride, N - nt * n_stride)) of W (n_stride = NT for a
 // dense layer, C_out / groups for a grouped one, whose W already has K = C_in / groups rows).
+//
+// GROUPED layers with thin groups pack `gt` consecutive groups into one tile as a BLOCK-DIAGONAL weight (K = gt *
+// kin_g contraction channels, n_stride = gt * pout_g produced channels, zeros off the diagonal): a 128->256 g16
+// layer (8 -> 16 channels per group) becomes 2 tiles of K = 64 x N = 128 instead of 16 tiles of K = 8 (padded to
+// 16) x N = 16 -- 8x fewer tiles, each restaging the activations once, at MMA shapes the tensor pipe runs well.
+// w is then [taps][kin_g][N] (rows = channels of ONE group) and K = gt * kin_g; kin_g = 0 means dense.
 __global__ void tc_pack_weights_kernel(const float* __restrict__ w, int taps, int K, int N, int NT, int n_stride,
-                                       int ntiles, __nv_bfloat16* __restrict__ out) {
+                                       int ntiles, int kin_g, int pout_g, __nv_bfloat16* __restrict__ out) {
   const int kchunks = (K + kTcKC - 1) / kTcKC;
   const long long total = (long long)taps * kchunks * ntiles * NT * kTcKC;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -57,8 +63,15 @@ __global__ void tc_pack_weights_kernel(const float* __restrict__ w, int taps, in
     const int j = (int)(block / ((long long)ntiles * kchunks));
     const int k = kc * kTcKC + c;
     const int n = nt * n_stride + r;
-    const bool ok = k < K && r < n_stride && n < N;
-    const float x = ok ? w[((long long)j * K + k) * N + n] : 0.f;
+    bool ok = k < K && r < n_stride && n < N;
+    long long src;
+    if (kin_g > 0) {   // block diagonal: contraction channel k and produced channel r must be in the same group
+      ok = ok && (k / kin_g) == (r / pout_g);
+      src = ((long long)j * kin_g + (k % kin_g)) * N + n;
+    } else {
+      src = ((long long)j * K + k) * N + n;
+    }
+    const float x = ok ? w[src] : 0.f;
     const __nv_bfloat16 hi = __float2bfloat16_rn(x);
     const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
     const long long base = block * (2LL * NT * kTcKC);
@@ -102,7 +115,9 @@ struct TcParams {
   int tap_shift[kMaxTaps];            // image row shift (q_n - q_lo) * nsub
 };
 
-constexpr int kTcThreads = 320;  // warps 0-3 stage activations, 4 streams weights, 5 issues MMAs, 6-9 epilogue
+// warps 0-3 and 10-13 stage activations (two producer groups filling ALTERNATE pipeline stages, so two images'
+// worth of global loads are in flight), 4 streams weights, 5 issues MMAs, 6-9 epilogue
+constexpr int kTcThreads = 448;
 
 // Persistent: gridDim.x = min(#tiles, #SMs); each CTA walks tiles blockIdx.x, +gridDim.x, ...  The three
 // pipelines (activation images, weight tiles, TMEM accumulators: 2 buffers) run continuously ACROSS tiles,
@@ -143,8 +158,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   const uint32_t tmem_acc = *tmem_slot;
   const uint32_t buf_cols = (uint32_t)(p.tmem_cols / 2);
 
-  if (warp < 4) {
+  if (warp < 4 || warp >= 10) {
     // ===================== activation producers =====================
+    const int pg = warp < 4 ? 0 : 1;                 // producer group: stages it = pg, pg + 2, ...
+    const int ptid = warp < 4 ? tid : tid - 320;     // 0..127 inside the group
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int gm = tile % mtiles, bb = tile / (mtiles * p.ntiles);
@@ -154,6 +171,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       const int f0 = (gm - p.ph_mt0[ph]) * kTcM;
       for (int c = 0; c < p.kchunks; ++c) {
         for (int g = p.ph_g0[ph]; g < p.ph_g0[ph + 1]; ++g, ++it) {
+          if ((it & 1) != pg) continue;
           const int s = it % p.na_stages;
           mbar_wait(&empty_a[s], ((it / p.na_stages) & 1) ^ 1);
           uint8_t* img_hi = a_base + (size_t)s * a_stage_bytes;
@@ -162,7 +180,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           rm.fv0 = f0 + p.grp_qlo[g] * p.nsub;
           rm.nsub = p.nsub; rm.step = p.i_step; rm.rho = p.grp_rho[g]; rm.up = p.up; rm.t_lim = p.t_in * p.up;
           stage_rows<5>(img_hi, img_hi + img_bytes, p.in, p.in.p, p.in.aux, p.c_in, ch_base + c * kTcKC,
-                        min(kTcKC, p.kg - c * kTcKC), false, rm, p.rows, tid);
+                        min(kTcKC, p.kg - c * kTcKC), false, rm, p.rows, ptid);
           fence_proxy_async();
           mbar_arrive(&full_a[s]);
         }
@@ -346,6 +364,7 @@ struct TcLayerPlan {
   int n_stride;  // produced channels per N tile
   int NT;        // padded N tile (multiple of 16, <= 256)
   int ntiles, kchunks, grouped;
+  int kin_g, pout_g;   // grouped: channels of ONE group on the contraction / produced side (kg = gt * kin_g)
 };
 
 static TcLayerPlan layer_plan(const KtConv1dDesc* d, int dir) {
@@ -359,7 +378,13 @@ static TcLayerPlan layer_plan(const KtConv1dDesc* d, int dir) {
   L.grouped = g > 1;
   if (g > 1) {
     if (pout > 256) return L;
-    L.n_stride = pout; L.NT = (pout + 15) & ~15; L.ntiles = g;
+    // groups per tile: fill one 64-channel K chunk, keep the N tile <= 128 (block-diagonal tile, see tc_pack_weights_kernel)
+    int gt = 1;
+    while (gt * 2 <= g && g % (gt * 2) == 0 && kin * gt * 2 <= kTcKC && pout * gt * 2 <= 128) gt *= 2;
+    L.kin_g = kin; L.pout_g = pout;
+    L.kg = gt * kin;
+    L.kchunks = ceil_div(L.kg, kTcKC);
+    L.n_stride = gt * pout; L.NT = (L.n_stride + 15) & ~15; L.ntiles = g / gt;
   } else if (pout <= 256) {
     L.n_stride = pout; L.NT = (pout + 15) & ~15; L.ntiles = 1;
     // under-filled grids (short sequences x wide layers): split N so that >= ~1 tile per SM exists
@@ -448,7 +473,10 @@ static bool plan_launches(const std::vector<Phase>& phases, int nsub, std::vecto
 }
 
 // Is (direction dir: 0 fwd, 1 bwd_data) of this layer runnable on the tcgen05 kernel?  -> N tile or 0
+bool thin_cin1_ok(const KtConv1dDesc* d);   // thin.cu
+
 int tc_plan(const KtConv1dDesc* d, int dir) {
+  if (dir == 0 && d->path != KT_PATH_TC && thin_cin1_ok(d)) return 0;   // waveform-input layers: HBM-bound FIR kernel
   if (dir == 1 && d->upsample > 1) return 0;          // `upsample` single-tap residue phases: staging-bound, stays FFMA
   const TcLayerPlan L = layer_plan(d, dir);
   if (!L.ok) return 0;
@@ -471,7 +499,7 @@ int tc_pack_layer(const KtConv1dDesc* d, int dir, const float* w, void* out, cud
   const long long total = (long long)d->kernel * L.kchunks * L.ntiles * L.NT * kTcKC;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
   tc_pack_weights_kernel<<<blocks, 256, 0, st>>>(w, d->kernel, L.kg, L.n_total, L.NT, L.n_stride, L.ntiles,
-                                                 reinterpret_cast<__nv_bfloat16*>(out));
+                                                 L.grouped ? L.kin_g : 0, L.pout_g, reinterpret_cast<__nv_bfloat16*>(out));
   KT_CHECK_CUDA(cudaGetLastError());
   return KT_OK;
 }

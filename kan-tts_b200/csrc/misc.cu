@@ -50,6 +50,39 @@ __global__ void add3_scale_kernel(const float* __restrict__ a, const float* __re
     y[i] = scale * (a[i] + (b ? b[i] : 0.f) + (c ? c[i] : 0.f));
 }
 
+// Data gradient of `nn.Upsample(nearest, scale) -> LeakyReLU -> conv` (hifigan.py:82-97) in two steps: the plain
+// conv data gradient wrt the (never materialised in forward) up-sampled rows runs on the tcgen05 kernel, then
+//   dx[r][c] = act_in'(x[r][c]) * sum_{u < up} dxu[r*up + u][c]
+// folds the `up` replicated rows back (bound: HBM, reads up*rows*C + rows*C floats once).
+__global__ void upsample_grad_reduce_kernel(const float* __restrict__ dxu, const float* __restrict__ x, int act,
+                                            float slope, float* __restrict__ dx, long long rows, int up, int c4) {
+  const long long total = rows * c4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / c4;
+    const int q = (int)(i % c4);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < up; ++u) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(dxu) + (r * up + u) * c4 + q);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (act == KT_ACT_LRELU) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x) + i);
+      acc.x = xv.x > 0.f ? acc.x : acc.x * slope; acc.y = xv.y > 0.f ? acc.y : acc.y * slope;
+      acc.z = xv.z > 0.f ? acc.z : acc.z * slope; acc.w = xv.w > 0.f ? acc.w : acc.w * slope;
+    }
+    reinterpret_cast<float4*>(dx)[i] = acc;
+  }
+}
+
+int upsample_grad_reduce(const float* dxu, const float* x, int act, float slope, float* dx, long long rows, int up, int c,
+                         cudaStream_t st) {
+  KT_REQUIRE(dxu && dx && rows > 0 && up >= 1 && c > 0 && (c & 3) == 0, "upsample_grad_reduce: bad arguments (C %% 4 == 0 required)");
+  KT_REQUIRE(act == KT_ACT_NONE || (act == KT_ACT_LRELU && x), "upsample_grad_reduce: act must be NONE or LRELU (with x)");
+  upsample_grad_reduce_kernel<<<stream_grid(rows * (c / 4), 256), 256, 0, st>>>(dxu, x, act, slope, dx, rows, up, c / 4);
+  KT_CHECK_CUDA(cudaGetLastError());
+  return KT_OK;
+}
+
 // db3 analysis filters (PyWavelets Wavelet('db3').dec_lo / dec_hi)
 __constant__ float c_dec_lo[6] = {0.035226291882100656f, -0.08544127388224149f, -0.13501102001039084f,
                                   0.4598775021193313f, 0.8068915093133388f, 0.3326705529509569f};

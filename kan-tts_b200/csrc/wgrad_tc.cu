@@ -26,7 +26,9 @@ namespace kt {
 using namespace tc;
 
 constexpr int kWgTK = 64;        // flattened rows per staged chunk
-constexpr int kWgThreads = 192;
+// warps 0-3: producers of the even chunks + epilogue; 4: TMEM alloc; 5: MMA issuer; 6-9: producers of the odd chunks
+// (each producer group owns one of the two pipeline stages, so two chunks' global loads are in flight)
+constexpr int kWgThreads = 320;
 constexpr int kWgMaxUnits = 8;
 constexpr int kWgMaxGroups = 24;
 
@@ -34,7 +36,10 @@ struct WgTcParams {
   Side a, b;
   float* ws;
   int batch, nsub, t_a, t_b, ca, cb, taps_total;   // ca / cb = tensor widths (all groups)
-  int groups, ca_g, cb_g;                           // channels per group (= ca, cb when groups == 1)
+  int groups, ca_g, cb_g;                           // channels per (super-)group (= ca, cb when groups == 1)
+  // thin groups: `gt` consecutive conv groups form one super-group whose dense (gt*ca_g0) x (gt*cb_g0) product is
+  // computed and only the gt diagonal (ca_g0 x cb_g0) blocks are stored (cf. the block-diagonal tiles of conv_tc.cu)
+  int gt, ca_g0, cb_g0;
   int M;                       // base rows m per sub-sequence
   int step, up;
   int mode, NT, n_cb_tiles, n_ca_tiles;
@@ -90,11 +95,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 4 || warp >= 6) {
     // ===================== producers =====================
+    const int pg = warp < 4 ? 0 : 1;
+    const int ptid = warp < 4 ? tid : tid - 192;
     int it = 0;
     for (long long c = c_begin; c < c_end; ++c, ++it) {
       const int s = it & 1;
+      if (s != pg) continue;
       mbar_wait(&empty[s], ((it >> 1) & 1) ^ 1);
       const int bb = (int)(c / p.chunks_per_batch);
       const int f0 = (int)(c % p.chunks_per_batch) * kWgTK;
@@ -107,7 +115,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         uint8_t* hi = st + (size_t)g * 2 * img_a;
         const int c_lo = ca_tile * (p.mode == 0 ? 128 : 64) + g * 64;           // channel offset inside the group
         stage_rows<5>(hi, hi + img_a, p.a, p.a.p, p.a.aux, p.ca, cgrp * p.ca_g + c_lo, min(64, p.ca_g - c_lo), true, ra,
-                      p.rows_a, tid);
+                      p.rows_a, ptid);
       }
       RowMap rb;  // base side: rows m (flattened with w), zero beyond M
       rb.base_row = (long long)bb * p.t_b * p.nsub;
@@ -117,13 +125,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         uint8_t* hi = bst + (size_t)g * 2 * img_b;
         const int c_lo = cb_tile * p.NT + g * 64;
         stage_rows<4>(hi, hi + img_b, p.b, p.b.p, p.b.aux, p.cb, cgrp * p.cb_g + c_lo, min(64, p.cb_g - c_lo), true, rb,
-                      kWgTK, tid);
+                      kWgTK, ptid);
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);
     }
 
-    // ===================== epilogue: TMEM -> workspace partial tiles =====================
+    // ===================== epilogue (warps 0-3): TMEM -> workspace partial tiles =====================
+    if (warp < 4) {
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const int row = warp * 32 + lane;  // M index inside the unit
@@ -134,25 +143,41 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       if (p.mode == 0) { tap_n = p.unit_tap0[u0 + u]; ca_idx = ca_tile * 128 + row; valid = true; }
       else { tap_n = p.unit_tap0[u0 + u] + (row >> 6); ca_idx = row & 63; valid = (row >> 6) < p.unit_ntaps[u0 + u]; }
       valid = valid && ca_idx < p.ca_g;
-      const int col0 = cb_tile * p.NT;                                    // first column inside the group
-      const long long obase = valid ? (((long long)split * p.taps_total + p.tap_j[tap_n]) * p.ca_g + ca_idx) * p.cb +
-                                          (long long)cgrp * p.cb_g + col0 : 0;
-      const bool vec = ((p.cb | p.cb_g) & 3) == 0;
+      const int col0 = cb_tile * p.NT;                                    // first column inside the (super-)group
+      // columns [c_lo, c_hi) of this tile are stored, column n at obase + n
+      int c_lo = 0, c_hi = min(p.NT, p.cb_g - col0);
+      long long obase = 0;
+      if (valid) {
+        if (p.gt > 1) {   // block diagonal: row of conv group gl keeps only that group's cb_g0 columns
+          const int gl = ca_idx / p.ca_g0, ci_l = ca_idx - gl * p.ca_g0;
+          c_lo = gl * p.cb_g0; c_hi = c_lo + p.cb_g0;
+          obase = (((long long)split * p.taps_total + p.tap_j[tap_n]) * p.ca_g0 + ci_l) * p.cb +
+                  ((long long)cgrp * p.gt + gl) * p.cb_g0 - c_lo;
+        } else {
+          obase = (((long long)split * p.taps_total + p.tap_j[tap_n]) * p.ca_g + ca_idx) * p.cb + (long long)cgrp * p.cb_g + col0;
+        }
+      }
+      const bool vec = ((p.cb | p.cb_g0) & 3) == 0;
       for (int n0 = 0; n0 < p.NT; n0 += 32) {
         uint32_t rr[32];
         tmem_ld32(t_lane + (uint32_t)(u * p.NT + n0), rr);
         tmem_ld_wait();
         if (valid) {
-          const int ncols = min(32, p.cb_g - col0 - n0);
-          if (vec) {
-            for (int e = 0; e < ncols; e += 4)
-              *reinterpret_cast<float4*>(p.ws + obase + n0 + e) =
-                  make_float4(__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
+          const int e0 = max(0, c_lo - n0), e1 = min(32, c_hi - n0);
+          if (vec) {   // (fully unrolled with predicates: rr[] must stay in registers)
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              if (e >= e0 && e < e1)
+                *reinterpret_cast<float4*>(p.ws + obase + n0 + e) =
+                    make_float4(__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
           } else {
-            for (int e = 0; e < ncols; ++e) p.ws[obase + n0 + e] = __uint_as_float(rr[e]);
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e >= e0 && e < e1) p.ws[obase + n0 + e] = __uint_as_float(rr[e]);
           }
         }
       }
+    }
     }
     tc_fence_before();
   } else if (warp == 5) {
@@ -247,6 +272,10 @@ static WgPlan make_plan(const KtConv1dDesc* d) {
   const int ca = tr ? d->c_out : d->c_in, cb = tr ? d->c_in : d->c_out;
   p.groups = d->groups;
   p.ca_g = ca / d->groups; p.cb_g = cb / d->groups;
+  p.ca_g0 = p.ca_g; p.cb_g0 = p.cb_g; p.gt = 1;
+  if (d->groups > 1 && (p.cb_g & 3) == 0) {   // pack thin groups into block-diagonal super-groups
+    while (p.groups % 2 == 0 && p.ca_g * 2 <= 64 && p.cb_g * 2 <= 256) { p.groups /= 2; p.ca_g *= 2; p.cb_g *= 2; p.gt *= 2; }
+  }
   p.batch = d->batch; p.nsub = d->nsub; p.ca = ca; p.cb = cb; p.taps_total = d->kernel;
   p.t_a = tr ? d->t_out : d->t_in;
   p.t_b = tr ? d->t_in : d->t_out;
@@ -309,16 +338,27 @@ static WgPlan make_plan(const KtConv1dDesc* d) {
   p.chunks_per_batch = ceil_div(p.M * p.nsub, kWgTK);
   const long long units = (long long)p.batch * p.chunks_per_batch;
   const long long base = (long long)p.groups * p.n_ca_tiles * p.n_cb_tiles * p.ngroups;
-  long long nsplit = std::max<long long>(1, (148 + base - 1) / base);
-  nsplit = std::min(nsplit, units);
+  // split-K factor: CTAs run one per SM in waves of ~148; minimise (waves x chunks per CTA) plus the cost of writing
+  // and re-reading one more partial copy of the gradient (in units of one chunk ~ 10 us; ~4 TB/s effective)
+  const double out_chunks = (double)p.taps_total * p.ca_g0 * cb * 8.0 / 4e12 / 10e-6;
+  long long nsplit = 1;
+  double best = 1e30;
+  for (long long ns = 1; ns <= std::min<long long>(units, 296); ++ns) {
+    const long long waves = (base * ns + 147) / 148;
+    const double cost = (double)waves * (double)((units + ns - 1) / ns) + (double)ns * out_chunks;
+    if (cost < best - 1e-9) { best = cost; nsplit = ns; }
+  }
   p.nsplit = (int)nsplit;
-  pl.ws_floats = nsplit * (long long)p.taps_total * p.ca_g * cb;
+  pl.ws_floats = nsplit * (long long)p.taps_total * p.ca_g0 * cb;
   pl.ok = true;
   return pl;
 }
 
 // floats of workspace needed by conv1d_bwd_weight_tc (0 = layer not supported)
+bool thin_cin1_ok(const KtConv1dDesc* d);   // thin.cu
+
 long long wgrad_tc_workspace(const KtConv1dDesc* d) {
+  if (d->path != KT_PATH_TC && thin_cin1_ok(d)) return 0;   // waveform-input layers: thin.cu
   const WgPlan pl = make_plan(d);
   return pl.ok ? pl.ws_floats : 0;
 }
@@ -348,7 +388,7 @@ int conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy,
   dim3 grid(p.groups * p.n_ca_tiles * p.n_cb_tiles, p.ngroups, p.nsplit);
   wgrad_tc_kernel<<<grid, kWgThreads, pl.smem, st>>>(p);
   KT_CHECK_CUDA(cudaGetLastError());
-  const long long n = (long long)p.taps_total * p.ca_g * p.cb;
+  const long long n = (long long)p.taps_total * p.ca_g0 * p.cb;
   const int blocks = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, 148LL * 8));
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dw, n, p.nsplit);
   KT_CHECK_CUDA(cudaGetLastError());

@@ -152,6 +152,18 @@ class ConvSpec:
     def w_numel(self):
         return self.kernel * (self.c_in // self.groups) * self.c_out
 
+    def without_upsample(self):
+        """The same conv over the already up-sampled rows (upsample = 1, no fused pre-activation): its data
+        gradient on the tcgen05 kernel + kt_upsample_grad_reduce replaces the FFMA data gradient of the
+        nearest-upsampled conv."""
+        s = self.__dict__.get("_noup")
+        if s is None:
+            s = ConvSpec(c_in=self.c_in, c_out=self.c_out, kernel=self.kernel, stride=self.stride, dilation=self.dilation,
+                         pad_left=self.pad_left, pad_right=self.pad_right, groups=self.groups, act_out=self.act_out,
+                         act_out_slope=self.act_out_slope, path=self.path)
+            self.__dict__["_noup"] = s
+        return s
+
 
 class PreparedWeight:
     """Kernel-layout copies of one layer's effective weight (w_fwd, w_bwd) + the weight-norm
@@ -336,8 +348,16 @@ class ConvFn(torch.autograd.Function):
         ctx.spec, ctx.d, ctx.nb = spec, db, nb
         ctx.w_bwd, ctx.norm = pw.w_bwd, pw.norm
         nt_b = _tc_tile(lib, spec, db, 1) if x.requires_grad else 0
+        ctx.d_up = None
+        if x.requires_grad and nt_b == 0 and spec.upsample > 1 and spec.c_in % 4 == 0 and not spec.transposed:
+            # data gradient wrt the up-sampled rows on the tcgen05 kernel, folded back by kt_upsample_grad_reduce
+            s2 = spec.without_upsample()
+            d2 = s2.desc(nb, nsub, t_in * spec.upsample)
+            nt2 = _tc_tile(lib, s2, d2, 1) if d2.t_out == d.t_out else 0
+            if nt2:
+                ctx.d_up, nt_b = d2, nt2
         ctx.nt_bwd = nt_b
-        ctx.img_bwd = pw.tc_image(spec, db, 1, nt_b) if nt_b else None
+        ctx.img_bwd = pw.tc_image(spec, ctx.d_up or db, 1, nt_b) if nt_b else None
         ctx.has_resid, ctx.has_bias, ctx.has_g = resid is not None, bias is not None, g is not None
         ctx.params = (v, g, bias)
         ctx.save_for_backward(x, y if spec.act_out != KT_ACT_NONE else None, v, g)
@@ -359,8 +379,19 @@ class ConvFn(torch.autograd.Function):
             x_, y_ = x, y
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)     # items >= nb stay unwritten: nothing differentiable consumes them
-            if ctx.nt_bwd:
+            if ctx.d_up is not None:
                 global _tc_launches
+                d2 = ctx.d_up
+                dxu = torch.empty((ctx.nb, d2.t_in * d2.nsub, spec.c_in), device=x.device, dtype=torch.float32)
+                with _timed("conv_dgrad_tc", spec, d):
+                    check(lib.kt_conv1d_bwd_data_tc(ctypes.byref(d2), ptr(dy), ptr(y_), ptr(ctx.img_bwd), None,
+                                                    ptr(dxu), st), "kt_conv1d_bwd_data_tc")
+                    check(lib.kt_upsample_grad_reduce(ptr(dxu), ptr(x_), spec.act_in, spec.act_in_slope, ptr(dx),
+                                                      ctx.nb * d.t_in * d.nsub, spec.upsample, spec.c_in, st),
+                          "kt_upsample_grad_reduce")
+                _tc_launches += 1
+                _count()
+            elif ctx.nt_bwd:
                 with _timed("conv_dgrad_tc", spec, d):
                     check(lib.kt_conv1d_bwd_data_tc(ctypes.byref(d), ptr(dy), ptr(y_), ptr(ctx.img_bwd), ptr(x_),
                                                     ptr(dx), st), "kt_conv1d_bwd_data_tc")

@@ -8,9 +8,9 @@ alter any result:
     the reference computes, all-reduces and then zeroes them (trainer.py:577-578);
   * losses are kept as device tensors; ``.item()`` is only called by ``losses_to_float``.
 
-Launch overhead: one step is ~3000 kernel launches from Python.  ``GanStep(..., cuda_graph=True)``
-captures the step into three CUDA graphs (generator fwd/bwd | generator Adam + discriminator fwd/bwd |
-discriminator Adam), split exactly at the two gradient exchanges, and replays them -- "CUDA streams
+Launch overhead: one step is ~2500 kernel launches from Python.  ``GanStep(..., cuda_graph=True)``
+captures the step into two CUDA graphs (generator fwd/bwd | no-grad generator fwd + discriminator fwd/bwd),
+split at the gradient exchanges (the Adam steps stay eager between them), and replays them -- "CUDA streams
 and graphs instead of a tracing compiler".  The captured work is identical to the eager step.
 
 Multi-GPU (one process per GPU, ``torch.distributed`` NCCL over NVLink/NVSwitch): the batch is
@@ -135,14 +135,18 @@ class GanStep:
         gen_loss.backward()
         self._join_streams(y)
 
-    def _seg_gopt_discriminator(self, y, x):
-        """generator Adam (trainer.py:547-553), then discriminator forward/backward (:556-580)"""
-        cfg, crit, model, log = self.config, self.criterion, self.model, self._log
+    def _seg_gopt(self):
+        """generator Adam (trainer.py:547-553)"""
+        cfg, model = self.config, self.model
         if self._g_active():
             if cfg["generator_grad_norm"] > 0:
                 torch.nn.utils.clip_grad_norm_(model["generator"].parameters(), cfg["generator_grad_norm"])
             self.optimizer["generator"].step()
             self.scheduler["generator"].step()
+
+    def _seg_discriminator(self, y, x):
+        """discriminator forward/backward on a re-generated y_ (trainer.py:556-580)"""
+        cfg, crit, model, log = self.config, self.criterion, self.model, self._log
         if self._d_active():
             with torch.no_grad():
                 y_ = model["generator"](x)
@@ -162,6 +166,10 @@ class GanStep:
                 fg.zero()
             dis_loss.backward()
             self._join_streams(y)
+
+    def _seg_gopt_discriminator(self, y, x):
+        self._seg_gopt()
+        self._seg_discriminator(y, x)
 
     def _can_pair(self):
         return self.pair_discriminators and all(hasattr(d, "forward_pair") for d in self.model["discriminator"].values())
@@ -203,11 +211,11 @@ class GanStep:
         self._log = {}
         return out
 
-    def invalidate_weight_caches(self):
-        """Forget every prepared (kernel-layout) weight: needed when eager launches follow graph replays,
-        because replays update parameters without bumping the Python-side tensor versions."""
-        from . import ops
-        mods = [self.model["generator"], *self.model["discriminator"].values()]
+    def invalidate_weight_caches(self, mods=None):
+        """Forget every prepared (kernel-layout) weight of ``mods`` (default: all models), so that the next forward
+        re-runs kt_weight_prepare / kt_weight_pack_tc (in place, into the same persistent buffers)."""
+        if mods is None:
+            mods = [self.model["generator"], *self.model["discriminator"].values()]
         for m in mods:
             for sub in m.modules():
                 c = getattr(sub, "_cache", None)
@@ -216,27 +224,27 @@ class GanStep:
 
     # ---- CUDA-graph replay -----------------------------------------------------------------------------------
     def _capture(self, y, x):
+        """Two CUDA graphs: (generator fwd/losses/bwd) and (no-grad generator fwd + discriminator fwd/bwd).  The
+        gradient exchanges and the three Adam steps run eagerly between / after them (a dozen foreach launches each;
+        graphs holding the optimizer steps crashed cudaGraphLaunch on the full-size model, profiles/r01_notes.md).
+        Each graph keeps its own memory pool; no tensor produced inside one graph is consumed by the other."""
         if not (self._g_active() and self._d_active()):
             raise RuntimeError("GanStep(cuda_graph=True): capture needs both phases active (steps >= start steps)")
-        for opt in [self.optimizer["generator"], *self.optimizer["discriminator"].values()]:
-            for grp in opt.param_groups:
-                if not grp.get("capturable", False):
-                    raise RuntimeError("GanStep(cuda_graph=True) needs optimizers built with capturable=True")
         self._static = (y.clone(), x.clone())
         sy, sx = self._static
         self._log = {}
         torch.cuda.synchronize()
-        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        # the weight re-preparation must be PART of the graph that first uses a model after its (eager) Adam step:
+        # g1 re-prepares the discriminators (updated at the end of the previous step), g2 the generator
+        self.invalidate_weight_caches(list(self.model["discriminator"].values()))
         with torch.cuda.graph(g1):
             self._seg_generator(sy, sx)
-        self.g_grads.all_reduce_mean()
-        with torch.cuda.graph(g2, pool=g1.pool()):
-            self._seg_gopt_discriminator(sy, sx)
-        for fg in self.d_grads.values():
-            fg.all_reduce_mean()
-        with torch.cuda.graph(g3, pool=g1.pool()):
-            self._seg_dopt()
-        self._graphs = (g1, g2, g3)
+        self.invalidate_weight_caches([self.model["generator"]])
+        with torch.cuda.graph(g2):
+            self._seg_discriminator(sy, sx)
+        self._graphs = (g1, g2)
+        self._log = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in self._log.items()}
         # stream capture only RECORDS the kernels: run the step for real by replaying what was captured
         return self._replay(y, x)
 
@@ -244,13 +252,14 @@ class GanStep:
         sy, sx = self._static
         sy.copy_(y, non_blocking=True)
         sx.copy_(x, non_blocking=True)
-        g1, g2, g3 = self._graphs
+        g1, g2 = self._graphs
         g1.replay()
         self.g_grads.all_reduce_mean()
+        self._seg_gopt()
         g2.replay()
         for fg in self.d_grads.values():
             fg.all_reduce_mean()
-        g3.replay()
+        self._seg_dopt()
         self.steps += 1
         return dict(self._log)
 

@@ -27,4 +27,5 @@ print("host enqueue ms/step:", [round(v, 1) for v in enq])
 print("wall incl. sync ms/step:", [round(v, 1) for v in tot])
 import cProfile, pstats
 pr = cProfile.Profile(); pr.enable(); step.step((y, x)); pr.disable(); torch.cuda.synchronize()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(25)
+pstats.Stats(pr).sort_stats("tottime").print_stats(45)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(40)
