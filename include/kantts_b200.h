@@ -259,6 +259,11 @@ int kt_rows_gather_fwd(const float* in, const int32_t* idx, float* out, int32_t 
 int kt_rows_gather_bwd(const float* dout, const int32_t* idx, const int32_t* start, const int32_t* count, float* din,
                        int32_t batch, int32_t t_out, int32_t t_in, int32_t c, void* stream);
 
+/* Development aid: when dev_buf is non-NULL, CTA 0 of every following kt_conv1d_{fwd,bwd_data}_tc launch records
+ * clock64() timestamps per role / tile / event into it (int64 [4 roles][16 tiles][4 events]; scripts/tc_trace.py).
+ * Process-global and not thread-safe; pass NULL to switch it off (the default). */
+int kt_debug_set_trace(void* dev_buf);
+
 /* library info */
 const char* kt_last_error(void);
 int kt_version(void);

@@ -22,6 +22,7 @@ int stft_mel_bwd(const KtMelDesc*, const float*, const float*, const float*, con
 long long wgrad_tc_workspace(const KtConv1dDesc*);
 int conv1d_bwd_weight_tc(const KtConv1dDesc*, const float*, const float*, const float*, float*, float*, float*, long long, cudaStream_t);
 int tc_plan(const KtConv1dDesc*, int);
+void debug_set_trace(long long*);
 long long tc_image_bytes(const KtConv1dDesc*, int);
 int tc_pack_layer(const KtConv1dDesc*, int, const float*, void*, cudaStream_t);
 int conv1d_fwd_tc(const KtConv1dDesc*, const float*, const void*, const float*, const float*, float*, cudaStream_t);
@@ -96,6 +97,10 @@ int kt_sinadd_fwd(const float* x, float* y, int64_t n, void* stream) { return kt
 int kt_sinadd_bwd(const float* x, const float* dy, float* dx, int64_t n, void* stream) { return kt::sinadd_bwd(x, dy, dx, n, ST(stream)); }
 int kt_add3_scale(const float* a, const float* b, const float* c, float scale, float* y, int64_t n, void* stream) {
   return kt::add3_scale(a, b, c, scale, y, n, ST(stream));
+}
+int kt_debug_set_trace(void* dev_buf) {
+  kt::debug_set_trace(reinterpret_cast<long long*>(dev_buf));
+  return KT_OK;
 }
 int kt_upsample_grad_reduce(const float* dxu, const float* x, int32_t act_in, float act_in_slope, float* dx, int64_t rows,
                             int32_t up, int32_t c, void* stream) {

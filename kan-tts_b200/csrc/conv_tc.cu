@@ -95,6 +95,11 @@ struct TcParams {
   int out_act;
   float out_slope;
   int NT, ntiles, kchunks, rows, na_stages, nb_stages, tmem_cols;
+  // 1: every (K chunk, tap) weight tile of the layer has its own shared-memory slot (slot = c * ntaps + n), loaded
+  // ONCE per CTA and reused by all of its tiles -- thin layers otherwise re-stream all taps per 128-row tile through
+  // a ring whose refill round trip (commit -> empty -> bulk copy -> full) bounds the MMA issue rate (measured
+  // 0.6-0.8 us per tap, profiles/r02_tc_trace.md)
+  int w_resident;
   int kg;        // contraction channels per tile (C_in, or C_in / groups)
   int grouped;   // 1: N tile nt = group nt (input channels [nt * kg, +kg), outputs [nt * n_stride, +n_stride))
   int n_stride;  // output channels advanced per N tile
@@ -113,7 +118,15 @@ struct TcParams {
   int ntaps;
   int tap_j[kMaxTaps];                // weight tap index, ordered by group
   int tap_shift[kMaxTaps];            // image row shift (q_n - q_lo) * nsub
+  // development aid (kt_debug_set_trace): CTA 0 records clock64() per role / tile / event, see scripts/tc_trace.py
+  long long* trace;
 };
+
+constexpr int kTraceTiles = 16, kTraceEvents = 4;
+__device__ __forceinline__ void trace_ev(const TcParams& p, int role, int tile_i, int ev) {
+  if (p.trace != nullptr && blockIdx.x == 0 && tile_i < kTraceTiles)
+    p.trace[(role * kTraceTiles + tile_i) * kTraceEvents + ev] = clock64();
+}
 
 // warps 0-3 and 10-13 stage activations (two producer groups filling ALTERNATE pipeline stages, so two images'
 // worth of global loads are in flight), 4 streams weights, 5 issues MMAs, 6-9 epilogue
@@ -174,6 +187,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           if ((it & 1) != pg) continue;
           const int s = it % p.na_stages;
           mbar_wait(&empty_a[s], ((it / p.na_stages) & 1) ^ 1);
+          if (ptid == 0) trace_ev(p, pg, it >> 1, 0);
           uint8_t* img_hi = a_base + (size_t)s * a_stage_bytes;
           RowMap rm;
           rm.base_row = (long long)bb * p.t_in * p.nsub;
@@ -183,12 +197,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                         min(kTcKC, p.kg - c * kTcKC), false, rm, p.rows, ptid);
           fence_proxy_async();
           mbar_arrive(&full_a[s]);
+          if (ptid == 0) trace_ev(p, pg, it >> 1, 1);
         }
       }
     }
   } else if (warp == 4) {
     // ===================== weight stream (bulk async copies) =====================
-    if (lane == 0) {
+    if (lane == 0 && p.w_resident) {
+      if ((int)blockIdx.x < total_tiles) {
+        for (int c = 0; c < p.kchunks; ++c)
+          for (int n = 0; n < p.ntaps; ++n) {
+            const int s = c * p.ntaps + n;
+            const long long block = ((long long)p.tap_j[n] * p.kchunks + c) * p.ntiles;   // ntiles == 1
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + block * (long long)b_stage_bytes;
+            mbar_arrive_expect_tx(&full_b[s], (uint32_t)b_stage_bytes);
+            bulk_g2s(b_base + (size_t)s * b_stage_bytes, src, (uint32_t)b_stage_bytes, &full_b[s]);
+          }
+      }
+    } else if (lane == 0) {
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = (tile / mtiles) % p.ntiles;
@@ -215,8 +241,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       int it_a = 0, it_b = 0, ti = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
         const int buf = ti & 1;
+        trace_ev(p, 2, ti, 0);
         mbar_wait(&tmem_empty[buf], ((ti >> 1) & 1) ^ 1);   // epilogue has drained this accumulator buffer
         tc_fence_after();
+        trace_ev(p, 2, ti, 1);
         const uint32_t d_tmem = tmem_acc + (uint32_t)buf * buf_cols;
         uint32_t acc = 0;
         int ph = 0;
@@ -227,11 +255,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             const int sa = it_a % p.na_stages;
             mbar_wait(&full_a[sa], (it_a / p.na_stages) & 1);
             tc_fence_after();
+            if (c == 0 && g == p.ph_g0[ph]) trace_ev(p, 2, ti, 2);
             const uint32_t a_hi = smem_u32(a_base + (size_t)sa * a_stage_bytes);
             const uint32_t a_lo = a_hi + (uint32_t)img_bytes;
             for (int n = p.grp_first[g]; n < p.grp_first[g + 1]; ++n, ++it_b) {
-              const int sb = it_b % p.nb_stages;
-              mbar_wait(&full_b[sb], (it_b / p.nb_stages) & 1);
+              const int sb = p.w_resident ? c * p.ntaps + n : it_b % p.nb_stages;
+              // (resident slots complete their single phase 0 once and stay complete)
+              mbar_wait(&full_b[sb], p.w_resident ? 0u : (uint32_t)((it_b / p.nb_stages) & 1));
               tc_fence_after();
               const uint32_t b_hi = smem_u32(b_base + (size_t)sb * b_stage_bytes);
               const uint32_t b_lo = b_hi + (uint32_t)(p.NT * 128);
@@ -247,12 +277,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                 umma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
                 umma_bf16(d_tmem, da_hi, db_hi, idesc, 1);
               }
-              umma_commit(&empty_b[sb]);
+              if (!p.w_resident) umma_commit(&empty_b[sb]);
             }
             umma_commit(&empty_a[sa]);
           }
         }
         umma_commit(&tmem_full[buf]);
+        trace_ev(p, 2, ti, 3);
       }
     }
     __syncwarp();
@@ -267,8 +298,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       const int mt = gm - p.ph_mt0[ph];
       const int F = p.ph_M[ph] * p.nsub;
       const int buf = ti & 1;
+      if (tid == 192) trace_ev(p, 3, ti, 0);
       mbar_wait(&tmem_full[buf], (ti >> 1) & 1);
       tc_fence_after();
+      if (tid == 192) trace_ev(p, 3, ti, 1);
       const int f = mt * kTcM + quarter * 32 + lane;
       const bool valid = f < F;
       const int m = valid ? (p.nsub == 1 ? f : f / p.nsub) : 0;
@@ -278,6 +311,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       const int n_valid = min(p.n_stride, p.c_out - nt * p.n_stride);   // real output channels of this tile
       const bool vec_out = ((n_valid | p.c_out | p.n_stride) & 3) == 0;
       const uint32_t t_lane = tmem_acc + (uint32_t)buf * buf_cols + ((uint32_t)(quarter * 32) << 16);
+      // forward: residual add; data gradient: act_in' mask -- never both (the scalar path handles the general case)
+      const float* side_p = p.resid ? p.resid : p.mask.p;
+      const bool side_is_mask = p.resid == nullptr;
+      const bool batched = valid && vec_out && !(p.resid && p.mask.p);
       for (int n0 = 0; n0 < p.NT; n0 += 32) {
         uint32_t rr[32];
         if (p.NT - n0 >= 32) {
@@ -288,14 +325,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int e = 0; e < 16; ++e) { rr[e] = r16[e]; rr[16 + e] = 0u; }
         }
+        // all side-tensor loads of this 32-column chunk are issued back to back (and before the TMEM load is
+        // waited for): a load -> add -> store chain per 16 bytes cost ~0.5 us x 8 per chunk (profiles/r02_tc_trace.md)
+        const int ncols = valid ? min(32, n_valid - n0) : 0;
+        float4 sd[8];
+        if (batched && side_p) {
+#pragma unroll
+          for (int e8 = 0; e8 < 8; ++e8)
+            sd[e8] = e8 * 4 < ncols ? __ldg(reinterpret_cast<const float4*>(side_p + obase + n0 + e8 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         tmem_ld_wait();
         if (n0 + 32 >= p.NT) {   // last TMEM read of this tile: hand the buffer back to the MMA issuer
           tc_fence_before();
           mbar_arrive(&tmem_empty[buf]);
+          if (tid == 192) trace_ev(p, 3, ti, 2);
         }
-        if (valid && !vec_out) {
+        if (valid && !batched) {
           // thin / unaligned tiles (C_out = 1, ...): scalar epilogue
-          const int ncols = min(32, n_valid - n0);
           for (int e = 0; e < ncols; ++e) {
             const long long o = obase + n0 + e;
             float v = __uint_as_float(rr[e]);
@@ -308,8 +354,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             p.out[o] = v;
           }
         } else if (valid) {
-          const int ncols = min(32, n_valid - n0);
-          for (int e = 0; e < ncols; e += 4) {
+#pragma unroll
+          for (int e8 = 0; e8 < 8; ++e8) {
+            const int e = e8 * 4;
+            if (e >= ncols) continue;
             const long long o = obase + n0 + e;
             float v[4] = {__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3])};
             if (p.bias) {
@@ -323,16 +371,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
               for (int z = 0; z < 4; ++z) v[z] = tanhf(v[z]);
             }
-            if (p.mask.p) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(p.mask.p + o));
-              v[0] = side_apply(v[0], a.x, p.mask.mode, p.mask.slope);
-              v[1] = side_apply(v[1], a.y, p.mask.mode, p.mask.slope);
-              v[2] = side_apply(v[2], a.z, p.mask.mode, p.mask.slope);
-              v[3] = side_apply(v[3], a.w, p.mask.mode, p.mask.slope);
-            }
-            if (p.resid) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(p.resid + o));
-              v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+            if (side_p) {
+              const float4 a = sd[e8];
+              if (side_is_mask) {
+                v[0] = side_apply(v[0], a.x, p.mask.mode, p.mask.slope);
+                v[1] = side_apply(v[1], a.y, p.mask.mode, p.mask.slope);
+                v[2] = side_apply(v[2], a.z, p.mask.mode, p.mask.slope);
+                v[3] = side_apply(v[3], a.w, p.mask.mode, p.mask.slope);
+              } else {
+                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+              }
             }
             if (p.accumulate) {
               const float4 a = *reinterpret_cast<const float4*>(p.out + o);
@@ -342,9 +390,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           }
         }
       }
+      if (tid == 192) trace_ev(p, 3, ti, 3);
     }
   }
 
+  if (warp == 4 && lane == 0 && p.w_resident && (int)blockIdx.x < total_tiles)
+    for (int s = 0; s < p.nb_stages; ++s) mbar_wait(&full_b[s], 0);   // no bulk copy may outlive the CTA
   tc_fence_before();
   __syncthreads();
   if (warp == 4) {
@@ -513,18 +564,31 @@ static int sm_count() {
   return n;
 }
 
+static long long* g_trace = nullptr;   // development aid, not thread-safe: set by kt_debug_set_trace
+void debug_set_trace(long long* dev_buf) { g_trace = dev_buf; }
+
 static int run_tc(TcParams p, cudaStream_t st) {   // p: phases already planned by plan_launches
+  p.trace = g_trace;
   p.tmem_cols = 32;
   while (p.tmem_cols < p.NT) p.tmem_cols <<= 1;
   p.tmem_cols *= 2;                                   // two accumulator buffers
   const int a_stage = 2 * p.rows * 128;
   const int b_stage = 2 * p.NT * 128;
-  const int budget = kMaxDynSmem - 1024 /*align slack*/ - 256 /*barriers*/;
-  p.na_stages = 3;
-  if (3 * a_stage + 3 * b_stage > budget) p.na_stages = 2;
-  p.nb_stages = std::min(6, (budget - p.na_stages * a_stage) / b_stage);
-  KT_REQUIRE(p.nb_stages >= 2, "conv_tc: shared memory budget exceeded (rows=%d NT=%d)", p.rows, p.NT);
-  const size_t smem = 1024 + (size_t)p.na_stages * a_stage + (size_t)p.nb_stages * b_stage + 256;
+  const int slots = p.ntaps * p.kchunks;                                      // weight tiles of the whole layer
+  const int bar_bytes = (2 * 3 + 2 * std::max(6, slots) + 4) * 8 + 16;
+  const int budget = kMaxDynSmem - 1024 /*align slack*/ - bar_bytes;
+  p.w_resident = 0;
+  if (p.ntiles == 1 && slots <= 160 && 2 * a_stage + slots * b_stage <= budget) {
+    p.w_resident = 1;
+    p.nb_stages = slots;
+    p.na_stages = (budget - slots * b_stage) / a_stage >= 3 ? 3 : 2;
+  } else {
+    p.na_stages = 3;
+    if (3 * a_stage + 3 * b_stage > budget) p.na_stages = 2;
+    p.nb_stages = std::min(6, (budget - p.na_stages * a_stage) / b_stage);
+  }
+  KT_REQUIRE(p.nb_stages >= 2 || p.w_resident, "conv_tc: shared memory budget exceeded (rows=%d NT=%d)", p.rows, p.NT);
+  const size_t smem = 1024 + (size_t)p.na_stages * a_stage + (size_t)p.nb_stages * b_stage + bar_bytes;
   static std::atomic<bool> cfg{false};
   if (!cfg.load(std::memory_order_acquire)) {
     KT_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));

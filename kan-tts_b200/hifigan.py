@@ -50,6 +50,23 @@ def join_side_streams(device=None):
         cur = torch.cuda.current_stream(torch.device(dev_type, dev_index))
         for s in pool:
             cur.wait_stream(s)
+    ops.join_wgrad_streams(device)
+
+
+def prefetch_weights(module, streams):
+    """Launch the weight preparation of every weight-normed / plain conv of ``module`` on ``streams`` (round-robin,
+    one contiguous share of the layers per stream).  The caller forks the streams off the current one before and
+    joins them before the module's next forward.  Spectral-normed layers recompute their weight per forward."""
+    layers = [m for m in module.modules() if isinstance(m, _NormedConv) and m.norm != "spectral" and m._cache.last is not None]
+    n = len(streams)
+    for i, s in enumerate(streams):
+        share = layers[i::n]
+        if not share:
+            continue
+        with torch.cuda.stream(s):
+            for m in share:
+                v, g = m.effective_weight()
+                ops.prefetch_weight(m._cache, m.spec, v, g)
 
 
 def _split_pair(outs, fmaps, nb, detach_b):

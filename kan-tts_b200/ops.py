@@ -169,11 +169,12 @@ class PreparedWeight:
     """Kernel-layout copies of one layer's effective weight (w_fwd, w_bwd) + the weight-norm
     row norms, valid for one (parameter version) -- see kt_weight_prepare."""
 
-    __slots__ = ("w_fwd", "w_bwd", "norm", "key", "img", "img_stale")
+    __slots__ = ("w_fwd", "w_bwd", "norm", "key", "img", "img_stale", "last")
 
     def __init__(self):
         self.w_fwd = self.w_bwd = self.norm = None
         self.key = None
+        self.last = None       # (d, nt_fwd, d_bwd, nt_bwd) of the latest forward: what prefetch() re-prepares
         self.img = {}          # (dir, n_tile) -> packed split-bf16 tcgen05 weight tiles
         self.img_stale = set()
 
@@ -194,6 +195,20 @@ class PreparedWeight:
             _count()
             self.img_stale.discard(k)
         return img
+
+
+def prefetch_weight(cache, spec, v, g):
+    """Re-prepare (weight norm + layouts + tcgen05 tiles) a layer's weights ahead of its next forward, for the
+    shapes its latest forward used -- a no-op when nothing changed.  train.GanStep runs this for a whole model on
+    side streams right after that model's optimizer step, off the critical path of the other model's forward."""
+    if cache.last is None:
+        return
+    d, nt, db, nt_b = cache.last
+    pw = prepare_weight(cache, spec, v, g)
+    if nt and not (_FORCE_FFMA or spec.path == KT_PATH_FFMA):
+        pw.tc_image(spec, d, 0, nt)
+    if nt_b and not (_FORCE_FFMA or spec.path == KT_PATH_FFMA):
+        pw.tc_image(spec, db, 1, nt_b)
 
 
 def prepare_weight(cache, spec, v, g):
@@ -263,6 +278,33 @@ def mark_direct_grad(param, flag=True):
     engine's one ``grad += new`` launch per parameter per backward.  Unmarked parameters (DistributedDataParallel,
     plain ``loss.backward()`` users) receive their gradients through autograd as usual."""
     param._kt_direct = bool(flag)
+
+
+_WGRAD_ASYNC = os.environ.get("KANTTS_B200_WGRAD_STREAMS", "1") != "0"
+_WG_POOL = {}
+_wg_next = 0
+
+
+def _wgrad_stream(device):
+    """Round-robin over a small per-device pool of streams for the weight-gradient chains (wgrad, split-K reduce,
+    bias column sums, weight-norm backward + accumulation): they are leaves of the backward graph, so only the
+    data gradients stay on the critical path and the weight gradients fill otherwise idle SMs."""
+    global _wg_next
+    pool = _WG_POOL.setdefault((device.type, device.index), [])
+    if not pool:
+        pool.extend(torch.cuda.Stream(device=device) for _ in range(4))
+    _wg_next = (_wg_next + 1) % len(pool)
+    return pool[_wg_next]
+
+
+def join_wgrad_streams(device=None):
+    """The current stream waits for the weight-gradient streams (call after backward, before reading .grad)."""
+    for (dev_type, dev_index), pool in _WG_POOL.items():
+        if device is not None and (dev_type, dev_index) != (device.type, device.index):
+            continue
+        cur = torch.cuda.current_stream(torch.device(dev_type, dev_index))
+        for s in pool:
+            cur.wait_stream(s)
 
 
 def _is_direct(p):
@@ -360,6 +402,11 @@ class ConvFn(torch.autograd.Function):
         ctx.img_bwd = pw.tc_image(spec, ctx.d_up or db, 1, nt_b) if nt_b else None
         ctx.has_resid, ctx.has_bias, ctx.has_g = resid is not None, bias is not None, g is not None
         ctx.params = (v, g, bias)
+        prev = cache.last
+        if nt_b == 0 and prev is not None and prev[3]:     # a no-grad forward keeps the data-gradient plan to prefetch
+            cache.last = (d, nt, prev[2], prev[3])
+        else:
+            cache.last = (d, nt, ctx.d_up or db, nt_b)
         ctx.save_for_backward(x, y if spec.act_out != KT_ACT_NONE else None, v, g)
         return y
 
@@ -406,45 +453,60 @@ class ConvFn(torch.autograd.Function):
         need_w = ctx.needs_input_grad[3] or (ctx.has_g and ctx.needs_input_grad[4])
         need_b = ctx.has_bias and ctx.needs_input_grad[2]
         if need_w or need_b:
-            dw = torch.empty(spec.w_numel, device=x.device, dtype=torch.float32)
-            if need_b:
-                dbias = torch.empty(spec.c_out, device=x.device, dtype=torch.float32)
-            ws_floats = _wgrad_tc_workspace(lib, spec, d)
-            if ws_floats:
-                ws = torch.empty(ws_floats, device=x.device, dtype=torch.float32)
-                with _timed("conv_wgrad_tc", spec, d):
-                    check(lib.kt_conv1d_bwd_weight_tc(ctypes.byref(d), ptr(x_), ptr(dy), ptr(y_), ptr(dw), ptr(dbias),
-                                                      ptr(ws), ws_floats, st), "kt_conv1d_bwd_weight_tc")
-                _tc_launches += 1
-            else:
-                with _timed("conv_wgrad_ffma", spec, d):
-                    check(lib.kt_conv1d_bwd_weight(ctypes.byref(d), ptr(x_), ptr(dy), ptr(y_), ptr(dw), ptr(dbias), st),
-                          "kt_conv1d_bwd_weight")
-            _count(4 if need_b else 2)
-            if need_w:
-                pv, pg, pb = ctx.params
-                vd = v.detach().contiguous()
-                gd = None if g is None else g.detach().contiguous()
-                mode = 1 if ctx.has_g else 0
-                direct = (pv.is_leaf and _is_direct(pv) and _is_direct(pg) and (not need_b or _is_direct(pb))
-                          and ctx.needs_input_grad[3] and (not ctx.has_g or ctx.needs_input_grad[4]))
-                if direct:
-                    # AccumulateGrad folded into the kernel: param.grad += (train.FlatGrads buffers, pre-zeroed)
-                    check(lib.kt_weight_grad_accum(ptr(dw), ptr(vd), ptr(gd), ptr(ctx.norm), None, mode, vd.shape[0],
-                                                   vd.shape[1], spec.kernel, int(spec.transposed), spec.groups,
-                                                   ptr(pv.grad), None if pg is None else ptr(pg.grad),
-                                                   ptr(dbias) if need_b else None,
-                                                   ptr(pb.grad) if need_b else None, spec.c_out if need_b else 0, st),
-                          "kt_weight_grad_accum")
-                    dbias = None
+            pv, pg, pb = ctx.params
+            direct = (need_w and pv.is_leaf and _is_direct(pv) and _is_direct(pg) and (not need_b or _is_direct(pb))
+                      and ctx.needs_input_grad[3] and (not ctx.has_g or ctx.needs_input_grad[4]))
+            side = _wgrad_stream(x.device) if (direct and _WGRAD_ASYNC) else None
+            if side is not None:
+                # nothing of this chain is handed back to autograd (the kernels accumulate into param.grad), so it
+                # runs on a side stream; join_wgrad_streams() orders it before the optimizer
+                side.wait_stream(torch.cuda.current_stream())
+                for t in (x_, dy, y_):
+                    if t is not None:
+                        t.record_stream(side)
+                cm = torch.cuda.stream(side)
+                cm.__enter__()
+                st = stream_ptr()
+            try:
+                dw = torch.empty(spec.w_numel, device=x.device, dtype=torch.float32)
+                if need_b:
+                    dbias = torch.empty(spec.c_out, device=x.device, dtype=torch.float32)
+                ws_floats = _wgrad_tc_workspace(lib, spec, d)
+                if ws_floats:
+                    ws = torch.empty(ws_floats, device=x.device, dtype=torch.float32)
+                    with _timed("conv_wgrad_tc", spec, d):
+                        check(lib.kt_conv1d_bwd_weight_tc(ctypes.byref(d), ptr(x_), ptr(dy), ptr(y_), ptr(dw), ptr(dbias),
+                                                          ptr(ws), ws_floats, st), "kt_conv1d_bwd_weight_tc")
+                    _tc_launches += 1
                 else:
-                    dv = torch.empty_like(vd)
-                    if ctx.has_g:
-                        dg = torch.empty_like(g)
-                    check(lib.kt_weight_grad(ptr(dw), ptr(vd), ptr(gd), ptr(ctx.norm), None, mode, vd.shape[0],
-                                             vd.shape[1], spec.kernel, int(spec.transposed), spec.groups, ptr(dv),
-                                             ptr(dg), st), "kt_weight_grad")
-                _count()
+                    with _timed("conv_wgrad_ffma", spec, d):
+                        check(lib.kt_conv1d_bwd_weight(ctypes.byref(d), ptr(x_), ptr(dy), ptr(y_), ptr(dw), ptr(dbias), st),
+                              "kt_conv1d_bwd_weight")
+                _count(4 if need_b else 2)
+                if need_w:
+                    vd = v.detach().contiguous()
+                    gd = None if g is None else g.detach().contiguous()
+                    mode = 1 if ctx.has_g else 0
+                    if direct:
+                        # AccumulateGrad folded into the kernel: param.grad += (train.FlatGrads buffers, pre-zeroed)
+                        check(lib.kt_weight_grad_accum(ptr(dw), ptr(vd), ptr(gd), ptr(ctx.norm), None, mode, vd.shape[0],
+                                                       vd.shape[1], spec.kernel, int(spec.transposed), spec.groups,
+                                                       ptr(pv.grad), None if pg is None else ptr(pg.grad),
+                                                       ptr(dbias) if need_b else None,
+                                                       ptr(pb.grad) if need_b else None, spec.c_out if need_b else 0, st),
+                              "kt_weight_grad_accum")
+                        dbias = None
+                    else:
+                        dv = torch.empty_like(vd)
+                        if ctx.has_g:
+                            dg = torch.empty_like(g)
+                        check(lib.kt_weight_grad(ptr(dw), ptr(vd), ptr(gd), ptr(ctx.norm), None, mode, vd.shape[0],
+                                                 vd.shape[1], spec.kernel, int(spec.transposed), spec.groups, ptr(dv),
+                                                 ptr(dg), st), "kt_weight_grad")
+                    _count()
+            finally:
+                if side is not None:
+                    cm.__exit__(None, None, None)
         return dx, dres, dbias, dv, dg, None, None
 
 

@@ -19,6 +19,8 @@ sharded by utterance, replicas are identical, and the only exchange is the gradi
 Gradients of each model live in one flat fp32 buffer (``.grad`` tensors are views into it), so the
 exchange is ONE in-place NCCL all-reduce per model per phase with no packing copies.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -84,7 +86,11 @@ class GanStep:
     def _seg_generator(self, y, x):
         """generator forward, losses, backward (trainer.py:473-546)"""
         cfg, crit, model, log = self.config, self.criterion, self.model, self._log
+        # the discriminators' weights changed at the end of the previous step: re-prepare them on side streams while
+        # the generator runs
+        pre = self._prefetch(list(model["discriminator"].values()), y) if self._d_active() else None
         y_ = model["generator"](x)
+        self._prefetch_join(pre)
         gen_loss = 0.0
         if crit.get("stft_loss", None):
             sc_loss, mag_loss = crit["stft_loss"](y_, y)
@@ -148,6 +154,7 @@ class GanStep:
         """discriminator forward/backward on a re-generated y_ (trainer.py:556-580)"""
         cfg, crit, model, log = self.config, self.criterion, self.model, self._log
         if self._d_active():
+            self._prefetch_join(self._prefetch([model["generator"]], y))    # generator weights changed just now
             with torch.no_grad():
                 y_ = model["generator"](x)
             dis_loss = 0.0
@@ -170,6 +177,29 @@ class GanStep:
     def _seg_gopt_discriminator(self, y, x):
         self._seg_gopt()
         self._seg_discriminator(y, x)
+
+    @staticmethod
+    def _prefetch(modules, t):
+        if not t.is_cuda or os.environ.get("KANTTS_B200_PREFETCH", "1") == "0":
+            return None
+        from . import hifigan
+        cur = torch.cuda.current_stream()
+        key = (t.device.type, t.device.index)
+        if key not in ops._WG_POOL:
+            ops._wgrad_stream(t.device)
+        streams = ops._WG_POOL[key]
+        for s in streams:
+            s.wait_stream(cur)
+        for m in modules:
+            hifigan.prefetch_weights(m, streams)
+        return streams
+
+    @staticmethod
+    def _prefetch_join(streams):
+        if streams:
+            cur = torch.cuda.current_stream()
+            for s in streams:
+                cur.wait_stream(s)
 
     def _can_pair(self):
         return self.pair_discriminators and all(hasattr(d, "forward_pair") for d in self.model["discriminator"].values())
@@ -365,6 +395,7 @@ class SambertStep:
         loss_total = mel_loss_ + mel_loss + dur_loss + pitch_loss + energy_loss
         self.grads.zero()
         loss_total.backward()
+        ops.join_wgrad_streams(loss_total.device if loss_total.is_cuda else None)
         self.grads.all_reduce_mean()
         if self.grad_clip is not None:
             torch.nn.utils.clip_grad_norm_(self.grads.params, self.grad_clip)

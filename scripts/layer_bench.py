@@ -57,6 +57,7 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--only", default=None)
     a = ap.parse_args()
+    only = None if a.only is None else a.only.split(",")
     for n in LAYERS:
-        if a.only is None or a.only == n:
+        if only is None or n in only:
             run(n, a.iters)

@@ -29,15 +29,16 @@ def test_cuda_graph_step_matches_eager(golden):
     batches = [(y, x), (y.flip(0), x.flip(0)), ((y * 0.5).contiguous(), x), (y, (x * 0.9).contiguous()),
                (y.roll(7, -1), x), (y, x)]
     eager, m_e = _build(g, cfg, False)
+    traj_e = [K.train.losses_to_float(eager.step(b)) for b in batches]
+    torch.cuda.synchronize()
     graph, m_g = _build(g, cfg, True)
-    for i, b in enumerate(batches):
-        le = K.train.losses_to_float(eager.step(b))
-        lg = K.train.losses_to_float(graph.step(b))      # steps 0-1 eager warm-up, 2 capture, 3+ replay
+    traj_g = [K.train.losses_to_float(graph.step(b)) for b in batches]   # steps 0-1 eager warm-up, 2 capture, 3+ replay
+    for i, (le, lg) in enumerate(zip(traj_e, traj_g)):
         for k in le:
             # two independent trajectories: fp32-atomic summation order differs run to run and a GAN step amplifies
-            # it, so only the first replayed steps are compared tightly; replay bugs (stale weight / input buffers)
-            # show up as O(1e-1) differences
-            tol = 3e-3 if i <= 3 else 3e-2
+            # it (the feature-matching value most of all), so only the first replayed steps are compared tightly;
+            # replay bugs (stale weight / input buffers) show up as O(1e-1) differences that keep growing
+            tol = (3e-3 if i <= 3 else 3e-2) * (5.0 if k == "feature_matching_loss" else 1.0)
             assert abs(le[k] - lg[k]) <= tol * max(1.0, abs(le[k])), (i, k, le[k], lg[k])
     assert graph._graphs is not None
     for k, v in m_e["generator"].state_dict().items():

@@ -59,6 +59,11 @@ CASES = {
     "tc_upsample_conv": (dict(c_in=128, c_out=64, kernel=7, pad_left=6, upsample=2, act_in=0.1), 2, 300, 0, False, True),
     "tc_deconv_128_64_k4s2": (dict(c_in=128, c_out=64, kernel=4, stride=2, transposed=True, crop=2, act_in=0.1), 2, 300, 0, True, True),
     "tc_deconv_256_128": (dict(c_in=256, c_out=128, kernel=16, stride=8, transposed=True, crop=8, act_in=0.1), 2, 32, 0, True, True),
+    # SAM-BERT nn.Linear shapes whose widths are not multiples of 64 (dec_out_proj 128->240, postnet 80->512, dec_in_proj 288->128)
+    "lin_128_240": (dict(c_in=128, c_out=240, kernel=1), 3, 70, 0, False, False),
+    "lin_80_512": (dict(c_in=80, c_out=512, kernel=1), 3, 70, 0, False, False),
+    "lin_288_128": (dict(c_in=288, c_out=128, kernel=1), 3, 70, 0, False, False),
+    "lin_512_80_k3": (dict(c_in=512, c_out=80, kernel=3, pad_left=1, pad_right=1), 3, 70, 0, False, False),
 }
 
 
@@ -123,6 +128,8 @@ def _run_case(name, force_ffma):
     assert rel_l2(_from_rows(y).cpu(), yo) < tol, ("y", rel_l2(_from_rows(y).cpu(), yo))
     assert rel_l2(_from_rows(xg.grad).cpu(), xo.grad) < tol, ("dx", rel_l2(_from_rows(xg.grad).cpu(), xo.grad))
     tol_w = 3e-4 if used_tc else 5e-5
+    if spec.c_out == 1:
+        tol_w = max(tol_w, 1e-4)       # a single-channel dg / dbias is ONE float summed with fp32 atomics
     assert rel_l2(vg.grad.cpu(), vo.grad) < tol_w, ("dv", rel_l2(vg.grad.cpu(), vo.grad))
     assert rel_l2(bg.grad.cpu(), bo.grad) < tol_w, "dbias"
     if wn:
