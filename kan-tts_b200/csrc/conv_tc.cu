@@ -135,6 +135,9 @@ constexpr int kTcThreads = 448;
 // Persistent: gridDim.x = min(#tiles, #SMs); each CTA walks tiles blockIdx.x, +gridDim.x, ...  The three
 // pipelines (activation images, weight tiles, TMEM accumulators: 2 buffers) run continuously ACROSS tiles,
 // so staging of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap.
+// SIMPLE = true: nsub == 1, up == 1, vectorisable channel counts, no tanh / accumulate -- the generator's resblock
+// convs, the scale discriminator and every SAM-BERT linear / conv (see stage_rows).  false: everything else.
+template <bool SIMPLE>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up (all image / tile bases 1024-byte aligned)
@@ -193,8 +196,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           rm.base_row = (long long)bb * p.t_in * p.nsub;
           rm.fv0 = f0 + p.grp_qlo[g] * p.nsub;
           rm.nsub = p.nsub; rm.step = p.i_step; rm.rho = p.grp_rho[g]; rm.up = p.up; rm.t_lim = p.t_in * p.up;
-          stage_rows<5>(img_hi, img_hi + img_bytes, p.in, p.in.p, p.in.aux, p.c_in, ch_base + c * kTcKC,
-                        min(kTcKC, p.kg - c * kTcKC), false, rm, p.rows, ptid);
+          stage_rows<5, SIMPLE>(img_hi, img_hi + img_bytes, p.in, p.in.p, p.in.aux, p.c_in, ch_base + c * kTcKC,
+                                min(kTcKC, p.kg - c * kTcKC), false, rm, p.rows, ptid);
           fence_proxy_async();
           mbar_arrive(&full_a[s]);
           if (ptid == 0) trace_ev(p, pg, it >> 1, 1);
@@ -203,7 +206,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
   } else if (warp == 4) {
     // ===================== weight stream (bulk async copies) =====================
-    if (lane == 0 && p.w_resident) {
+    const bool leader = elect_one();
+    if (leader && p.w_resident) {
       if ((int)blockIdx.x < total_tiles) {
         for (int c = 0; c < p.kchunks; ++c)
           for (int n = 0; n < p.ntaps; ++n) {
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             bulk_g2s(b_base + (size_t)s * b_stage_bytes, src, (uint32_t)b_stage_bytes, &full_b[s]);
           }
       }
-    } else if (lane == 0) {
+    } else if (leader) {
       int it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = (tile / mtiles) % p.ntiles;
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     __syncwarp();
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(kTcM, p.NT, 0, 0);
       int it_a = 0, it_b = 0, ti = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
@@ -309,7 +313,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       const int to = p.ph_ooff[ph] + p.o_step * m;
       const long long obase = (((long long)bb * p.t_out + to) * p.nsub + w) * p.c_out + (long long)nt * p.n_stride;
       const int n_valid = min(p.n_stride, p.c_out - nt * p.n_stride);   // real output channels of this tile
-      const bool vec_out = ((n_valid | p.c_out | p.n_stride) & 3) == 0;
+      const bool vec_out = SIMPLE || ((n_valid | p.c_out | p.n_stride) & 3) == 0;
       const uint32_t t_lane = tmem_acc + (uint32_t)buf * buf_cols + ((uint32_t)(quarter * 32) << 16);
       // forward: residual add; data gradient: act_in' mask -- never both (the scalar path handles the general case)
       const float* side_p = p.resid ? p.resid : p.mask.p;
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           mbar_arrive(&tmem_empty[buf]);
           if (tid == 192) trace_ev(p, 3, ti, 2);
         }
-        if (valid && !batched) {
+        if (!SIMPLE && valid && !batched) {
           // thin / unaligned tiles (C_out = 1, ...): scalar epilogue
           for (int e = 0; e < ncols; ++e) {
             const long long o = obase + n0 + e;
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             if (p.out_act == KT_ACT_LRELU) {
 #pragma unroll
               for (int z = 0; z < 4; ++z) v[z] = v[z] > 0.f ? v[z] : v[z] * p.out_slope;
-            } else if (p.out_act == KT_ACT_TANH) {
+            } else if (!SIMPLE && p.out_act == KT_ACT_TANH) {
 #pragma unroll
               for (int z = 0; z < 4; ++z) v[z] = tanhf(v[z]);
             }
@@ -382,7 +386,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                 v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
               }
             }
-            if (p.accumulate) {
+            if (!SIMPLE && p.accumulate) {
               const float4 a = *reinterpret_cast<const float4*>(p.out + o);
               v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
             }
@@ -591,12 +595,17 @@ static int run_tc(TcParams p, cudaStream_t st) {   // p: phases already planned 
   const size_t smem = 1024 + (size_t)p.na_stages * a_stage + (size_t)p.nb_stages * b_stage + bar_bytes;
   static std::atomic<bool> cfg{false};
   if (!cfg.load(std::memory_order_acquire)) {
-    KT_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    KT_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+    KT_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     cfg.store(true, std::memory_order_release);
   }
   const long long tiles = (long long)p.ph_mt0[p.nphases] * p.ntiles * p.batch;
   const int grid = (int)std::min<long long>(tiles, sm_count());
-  conv_tc_kernel<<<grid, kTcThreads, smem, st>>>(p);
+  const bool simple = p.nsub == 1 && p.up == 1 && (p.kg & 7) == 0 && (p.c_in & 3) == 0 && (p.c_out & 3) == 0 &&
+                      (p.n_stride & 3) == 0 && p.out_act != KT_ACT_TANH && !p.accumulate &&
+                      (p.in.mode < SIDE_DLRELU || p.in.aux != nullptr) && !(p.resid && p.mask.p);
+  if (simple) conv_tc_kernel<true><<<grid, kTcThreads, smem, st>>>(p);
+  else conv_tc_kernel<false><<<grid, kTcThreads, smem, st>>>(p);
   KT_CHECK_CUDA(cudaGetLastError());
   return KT_OK;
 }

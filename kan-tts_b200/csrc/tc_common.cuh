@@ -13,6 +13,19 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One elected lane of a fully converged warp (elect.sync).  Unlike `if (lane == 0)`, the compiler knows that exactly
+// one thread runs the guarded region, so tcgen05.mma / bulk-copy operands move to uniform registers directly; with
+// the lane test every tcgen05.mma was wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -172,6 +185,13 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
 struct RowMap {
   long long base_row;
   int fv0, nsub, step, rho, up, t_lim;
+  // nsub == 1 && up == 1 (every layer but the period discriminator's and the nearest-upsampled convs): no divisions
+  __device__ __forceinline__ bool map_simple(int r, long long& row) const {
+    const int tv = (fv0 + r) * step + rho;
+    if (tv < 0 || tv >= t_lim) return false;
+    row = base_row + tv;
+    return true;
+  }
   __device__ __forceinline__ bool map(int r, long long& row) const {
     const int fv = fv0 + r;
     const int mp = nsub == 1 ? fv : fdiv(fv, nsub);
@@ -188,7 +208,7 @@ struct RowMap {
 // converts and stores.  The two phases are separate fully-unrolled loops without early exits: with one
 // CTA per SM the staging loop is pure DRAM/L2 latency, and a fused load->convert->store loop measured
 // ~1 load in flight per thread (profiles/r01_notes.md).
-template <int NB, bool VEC, bool AUX>
+template <int NB, bool VEC, bool AUX, bool SIMPLE = false>
 __device__ __forceinline__ void stage_rows_impl(uint8_t* img_hi, uint8_t* img_lo, const Side& s, const float* base,
                                                 const float* aux_base, int c_total, int ch0, int nv, const RowMap& rm,
                                                 int rows, int tid) {
@@ -201,7 +221,7 @@ __device__ __forceinline__ void stage_rows_impl(uint8_t* img_hi, uint8_t* img_lo
     for (int i = 0; i < NB; ++i) {
       const int r = r0 + 16 * i;
       long long srow = 0;
-      ok[i] = r < rows && nv > 0 && rm.map(r, srow);
+      ok[i] = r < rows && nv > 0 && (SIMPLE ? rm.map_simple(r, srow) : rm.map(r, srow));
       off[i] = ok[i] ? srow * c_total + ch0 + q * 8 : 0;   // offset 0 is always a readable address
     }
 #pragma unroll
@@ -253,7 +273,10 @@ __device__ __forceinline__ void stage_rows_impl(uint8_t* img_hi, uint8_t* img_lo
   }
 }
 
-template <int NB>
+// SIMPLE: the host guarantees nsub == 1, up == 1 and 16-byte-aligned 8-channel chunks (c_valid % 8 == 0, c_total % 4
+// == 0): only the vectorised instantiations exist in that kernel variant, which roughly halves its code size -- the
+// generic kernel (~140 KB of SASS shared by four concurrently running warp roles) does not fit the instruction cache.
+template <int NB, bool SIMPLE = false>
 __device__ __forceinline__ void stage_rows(uint8_t* img_hi, uint8_t* img_lo, const Side& s, const float* base,
                                            const float* aux_base, int c_total, int ch0, int c_valid, bool fill_all,
                                            const RowMap& rm, int rows, int tid) {
@@ -266,6 +289,11 @@ __device__ __forceinline__ void stage_rows(uint8_t* img_hi, uint8_t* img_lo, con
   const int nv = min(8, c_valid - q * 8);                       // valid channels of this thread's chunk (may be <= 0)
   const bool vec = nv == 8 && (c_total & 3) == 0 && ((ch0 + q * 8) & 3) == 0;
   const bool has_aux = s.mode >= SIDE_DLRELU;
+  if constexpr (SIMPLE) {
+    if (has_aux) stage_rows_impl<NB, true, true, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
+    else stage_rows_impl<NB, true, false, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
+    return;
+  }
   if (vec) {
     if (has_aux) stage_rows_impl<NB, true, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
     else stage_rows_impl<NB, true, false>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);

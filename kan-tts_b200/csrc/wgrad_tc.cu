@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     tc_fence_before();
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(128, p.NT, 1, 1);
       const uint32_t lbo_b = 2u * (uint32_t)img_b;
       int it = 0;
