@@ -191,7 +191,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--cpu-sample-batch", type=int, default=1)
+    ap.add_argument("--cpu-sample-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--launch", default="auto", choices=["auto", "graph", "eager"],
@@ -345,7 +345,7 @@ def main():
     if world > 1:
         dist.barrier()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"], _ = cpu_reference_run(1, 1, args.cpu_sample_batch)
+        line["cpu_baseline"], _ = cpu_reference_run(2, 1, args.cpu_sample_batch)      # ~15-20 s of CPU work
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -379,13 +379,20 @@ def roofline_leg(step, batch, ops, ms_per_step):
     # side streams OFF for this step: with concurrent streams an event pair around one launch also measures the
     # time the kernel spent queued behind other streams' kernels, i.e. not that kernel's own duration
     par, hifigan._PARALLEL_STREAMS = hifigan._PARALLEL_STREAMS, False
+    wga, ops._WGRAD_ASYNC = ops._WGRAD_ASYNC, False          # (the weight-gradient side streams as well)
+    pf = os.environ.get("KANTTS_B200_PREFETCH")
+    os.environ["KANTTS_B200_PREFETCH"] = "0"
     try:
         prof = ops.set_profiler(True)
         step._eager_step(*batch)
         summ = prof.summary()
     finally:
         ops.set_profiler(False)
-        hifigan._PARALLEL_STREAMS = par
+        hifigan._PARALLEL_STREAMS, ops._WGRAD_ASYNC = par, wga
+        if pf is None:
+            os.environ.pop("KANTTS_B200_PREFETCH", None)
+        else:
+            os.environ["KANTTS_B200_PREFETCH"] = pf
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         pk = json.load(open(peaks_path))

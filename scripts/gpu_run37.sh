@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench37_n2.log 2>&1; echo "n2 rc=$?"
+tail -n 3 gpurun_out/bench37_n2.log | cut -c1-1200
