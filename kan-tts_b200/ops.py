@@ -372,7 +372,6 @@ class ConvFn(torch.autograd.Function):
             assert resid.shape == y.shape, (resid.shape, y.shape)
         bd = None if bias is None else bias.detach()
         nt = _tc_tile(lib, spec, d, 0)
-        pass  # (algorithmic work is computed lazily by _timed when the profiler is on)
         if nt:
             global _tc_launches
             img = pw.tc_image(spec, d, 0, nt)
