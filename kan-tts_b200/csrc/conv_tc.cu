@@ -100,6 +100,11 @@ struct TcParams {
   // a ring whose refill round trip (commit -> empty -> bulk copy -> full) bounds the MMA issue rate (measured
   // 0.6-0.8 us per tap, profiles/r02_tc_trace.md)
   int w_resident;
+  // 1 (NT <= 128, NT % 32 == 0): the hi*hi and hi*lo products of a K slice are ONE tcgen05.mma -- the weight tile
+  // [hi rows | lo rows] is read as a single N = 2*NT operand, accumulator columns [0, NT) and [NT, 2*NT) -- plus one
+  // N = NT instruction for lo*hi; the epilogue adds the two column ranges.  A tcgen05.mma of this kernel costs
+  // ~130 cycles whatever N is (shared-memory A operand), so 2 instructions per slice instead of 3 is -1/3 MMA time.
+  int fuse2;
   int kg;        // contraction channels per tile (C_in, or C_in / groups)
   int grouped;   // 1: N tile nt = group nt (input channels [nt * kg, +kg), outputs [nt * n_stride, +n_stride))
   int n_stride;  // output channels advanced per N tile
@@ -242,6 +247,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     // ===================== MMA issuer =====================
     if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(kTcM, p.NT, 0, 0);
+      const uint32_t idesc2 = make_idesc_bf16(kTcM, 2 * p.NT, 0, 0);
       int it_a = 0, it_b = 0, ti = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
         const int buf = ti & 1;
@@ -257,16 +263,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           const int kslices = (min(kTcKC, p.kg - c * kTcKC) + 15) >> 4;   // K = 16 slices holding real channels
           for (int g = p.ph_g0[ph]; g < p.ph_g0[ph + 1]; ++g, ++it_a) {
             const int sa = it_a % p.na_stages;
+            // (no tcgen05.fence here or after the weight wait: the producers' fence.proxy.async + mbarrier release
+            //  / the bulk copy's complete_tx make the data visible to the MMA's async-proxy reads; a
+            //  fence::after_thread_sync per tap drained the MMA pipeline -- the MMA phase was ~constant per TAP,
+            //  not per instruction, profiles/r01_notes.md)
             mbar_wait(&full_a[sa], (it_a / p.na_stages) & 1);
-            tc_fence_after();
             if (c == 0 && g == p.ph_g0[ph]) trace_ev(p, 2, ti, 2);
             const uint32_t a_hi = smem_u32(a_base + (size_t)sa * a_stage_bytes);
             const uint32_t a_lo = a_hi + (uint32_t)img_bytes;
             for (int n = p.grp_first[g]; n < p.grp_first[g + 1]; ++n, ++it_b) {
               const int sb = p.w_resident ? c * p.ntaps + n : it_b % p.nb_stages;
               // (resident slots complete their single phase 0 once and stay complete)
+              if (ti == 1 && c == 0) trace_ev(p, 4, n & 15, 0);     // role 4: per-tap stamps of the MMA issuer, tile 1
               mbar_wait(&full_b[sb], p.w_resident ? 0u : (uint32_t)((it_b / p.nb_stages) & 1));
-              tc_fence_after();
+              if (ti == 1 && c == 0) trace_ev(p, 4, n & 15, 1);
               const uint32_t b_hi = smem_u32(b_base + (size_t)sb * b_stage_bytes);
               const uint32_t b_lo = b_hi + (uint32_t)(p.NT * 128);
               const uint32_t shift = (uint32_t)p.tap_shift[n] * 128u;
@@ -276,12 +286,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                 const uint64_t da_lo = smem_desc_sw128(a_lo + shift + ko, 16, 1024, false);
                 const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024, false);
                 const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 16, 1024, false);
-                umma_bf16(d_tmem, da_lo, db_hi, idesc, acc);
+                if (p.fuse2) {
+                  umma_bf16(d_tmem, da_hi, db_hi, idesc2, acc);     // [a_hi*b_hi | a_hi*b_lo] -> columns [0, 2*NT)
+                  umma_bf16(d_tmem, da_lo, db_hi, idesc, 1);        //  a_lo*b_hi             -> columns [0, NT)
+                } else {
+                  umma_bf16(d_tmem, da_lo, db_hi, idesc, acc);
+                  umma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
+                  umma_bf16(d_tmem, da_hi, db_hi, idesc, 1);
+                }
                 acc = 1;
-                umma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
-                umma_bf16(d_tmem, da_hi, db_hi, idesc, 1);
               }
+              if (ti == 1 && c == 0) trace_ev(p, 4, n & 15, 2);
               if (!p.w_resident) umma_commit(&empty_b[sb]);
+              if (ti == 1 && c == 0) trace_ev(p, 4, n & 15, 3);
             }
             umma_commit(&empty_a[sa]);
           }
@@ -339,6 +356,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             sd[e8] = e8 * 4 < ncols ? __ldg(reinterpret_cast<const float4*>(side_p + obase + n0 + e8 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         tmem_ld_wait();
+        if (p.fuse2) {   // + the hi*lo products (columns [NT, 2*NT)), 16 columns at a time (registers)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t t2[16];
+            tmem_ld16(t_lane + (uint32_t)(p.NT + n0 + 16 * h), t2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) rr[16 * h + e] = __float_as_uint(__uint_as_float(rr[16 * h + e]) + __uint_as_float(t2[e]));
+          }
+        }
         if (n0 + 32 >= p.NT) {   // last TMEM read of this tile: hand the buffer back to the MMA issuer
           tc_fence_before();
           mbar_arrive(&tmem_empty[buf]);
@@ -573,8 +600,9 @@ void debug_set_trace(long long* dev_buf) { g_trace = dev_buf; }
 
 static int run_tc(TcParams p, cudaStream_t st) {   // p: phases already planned by plan_launches
   p.trace = g_trace;
+  p.fuse2 = (p.NT <= 128 && p.NT % 32 == 0) ? 1 : 0;
   p.tmem_cols = 32;
-  while (p.tmem_cols < p.NT) p.tmem_cols <<= 1;
+  while (p.tmem_cols < (p.fuse2 ? 2 : 1) * p.NT) p.tmem_cols <<= 1;
   p.tmem_cols *= 2;                                   // two accumulator buffers
   const int a_stage = 2 * p.rows * 128;
   const int b_stage = 2 * p.NT * 128;
