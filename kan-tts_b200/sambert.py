@@ -202,6 +202,21 @@ class MultiHeadPNCAAttention(nn.Module):
         self.x_kv = None
         self.x_state_size = 0
 
+    def forward_step(self, x, h, step, mask_x, mask_h):
+        """Free-running decoding (update_x_state / update_h_state, sambert/__init__.py:212-267): x (B, 1, d_model) is
+        step ``step``'s input; the self keys / values of all steps live in ONE preallocated (B, Lmax, 3HD) buffer
+        (the reference grows them with torch.cat), the memory keys / values are projected at step 0."""
+        if step == 0 or self.h_kv is None:
+            self.h_kv = self.w_h_kv(h).contiguous()
+            self.x_kv = torch.zeros(x.shape[0], h.shape[1], 3 * self.n_head * self.d_head, device=x.device,
+                                    dtype=torch.float32)
+            self.x_state_size = 0
+        q_row = self.w_x_qkv(self.layer_norm(x)).contiguous()
+        self.x_kv[:, step:step + 1] = q_row
+        self.x_state_size = step + 1
+        ox, oh, attn_x, attn_h = sops.pnca_attn_step(q_row, self.x_kv, self.h_kv, mask_x, mask_h, self.n_head)
+        return self.fc_h(oh, resid=self.fc_x(ox, resid=x)), attn_x, attn_h
+
     def forward(self, x, h, mask_x=None, mask_h=None):
         x_qkv = self.w_x_qkv(self.layer_norm(x))
         h_kv = self.w_h_kv(h)
@@ -226,6 +241,15 @@ class PNCABlock(nn.Module):
 
     def forward(self, input, memory, mask=None, pnca_x_attn_mask=None, pnca_h_attn_mask=None):
         out, ax, ah = self.pnca_attn(input, memory, pnca_x_attn_mask, pnca_h_attn_mask)
+        if mask is not None:
+            out = out.masked_fill(mask.unsqueeze(-1), 0)
+        out = self.pos_ffn(out, mask=mask)
+        if mask is not None:
+            out = out.masked_fill(mask.unsqueeze(-1), 0)
+        return out, ax, ah
+
+    def forward_step(self, input, memory, step, mask=None, pnca_x_attn_mask=None, pnca_h_attn_mask=None):
+        out, ax, ah = self.pnca_attn.forward_step(input, memory, step, pnca_x_attn_mask, pnca_h_attn_mask)
         if mask is not None:
             out = out.masked_fill(mask.unsqueeze(-1), 0)
         out = self.pos_ffn(out, mask=mask)
@@ -540,7 +564,28 @@ class HybridAttentionDecoder(nn.Module):
         return self.dec_out_proj(self.ln(x)), ax_lst, ah_lst
 
     def infer(self, step, input, memory, x_band_width, h_band_width, mask=None, return_attns=False):
-        raise NotImplementedError("free-running PNCA decoding is not built yet (SURVEY.md section 8f item 1)")
+        """kantts_sambert.py:207-253: one decoder step; ``reset_state()`` must precede step 0.  The band masks are
+        built once per utterance (step 0) and sliced per step; any batch size (the reference's masks lose the batch
+        dimension, so it only runs batch 1)."""
+        max_len = memory.size(1)
+        if step == 0 or getattr(self, "_step_masks", None) is None or self._step_masks[0].shape[-1] != max_len:
+            _, mx, mh = self.get_pnca_attn_mask(memory.device, max_len, x_band_width, h_band_width, mask)
+            self._step_masks = (mx.contiguous(), mh.contiguous())
+        mx, mh = self._step_masks
+        x = self.dec_in_proj(torch.cat([memory[:, step:step + 1, :], self.prenet(input)], dim=-1))
+        x = x * self.d_model ** 0.5
+        x = _drop(x, self.dropout, self.training)
+        mask_step = None if mask is None else mask[:, step:step + 1]
+        ax_lst, ah_lst = [], []
+        for layer in self.pnca:
+            # (the self-attention mask row covers the whole preallocated key range: keys after `step` are masked)
+            x, ax, ah = layer.forward_step(x, memory, step, mask=mask_step,
+                                           pnca_x_attn_mask=mx[:, step:step + 1, :].contiguous(),
+                                           pnca_h_attn_mask=mh[:, step:step + 1, :].contiguous())
+            if return_attns:
+                ax_lst += [ax]
+                ah_lst += [ah]
+        return self.dec_out_proj(self.ln(x)), ax_lst, ah_lst
 
 
 class TextFftEncoder(nn.Module):
@@ -643,10 +688,28 @@ class MelPNCADecoder(nn.Module):
             config["decoder_relu_dropout"], self.d_mel * r)
 
     def forward(self, memory, x_band_width, h_band_width, target=None, mask=None, return_attns=False):
-        if target is None:
-            raise NotImplementedError("free-running PNCA decoding is not built yet (SURVEY.md section 8f item 1)")
         go_frame = torch.zeros((memory.size(0), 1, self.d_mel), device=memory.device)
         self.mel_dec.reset_state()
+        if target is None:
+            # free-running decoding (kantts_sambert.py:567-612): each step's last d_mel outputs feed the next step.
+            # Attention rows come back at the full key length (masked keys are exact zeros), which is what the
+            # reference builds by zero-padding every step's row before concatenating.
+            outs = []
+            ax_steps = [[] for _ in range(self.nb_layers)]
+            ah_steps = [[] for _ in range(self.nb_layers)]
+            inp = go_frame
+            for step in range(memory.size(1)):
+                out, ax, ah = self.mel_dec.infer(step, inp, memory, x_band_width, h_band_width, mask=mask,
+                                                 return_attns=return_attns)
+                inp = out[:, :, -self.d_mel:]
+                outs.append(out)
+                for i, (a, b) in enumerate(zip(ax, ah)):
+                    ax_steps[i].append(a)
+                    ah_steps[i].append(b)
+            dec = torch.cat(outs, dim=1)
+            if not return_attns:
+                return dec, [], []
+            return dec, [torch.cat(a, dim=1) for a in ax_steps], [torch.cat(a, dim=1) for a in ah_steps]
         inp = torch.cat([go_frame, target[:, self.r - 1:: self.r, :]], dim=1)[:, :-1, :]
         return self.mel_dec(inp, memory, x_band_width, h_band_width, mask=mask, return_attns=return_attns)
 

@@ -181,6 +181,35 @@ class PncaAttnFn(torch.autograd.Function):
         return dqkv, dhkv, None, None, None, None, None, None
 
 
+def pnca_attn_step(q_row, x_cache, h_kv, mask_x, mask_h, n_head):
+    """One free-running decoder step of MultiHeadPNCAAttention (sambert/__init__.py:212-300), inference only.
+    q_row (B, 1, 3HD): this step's fused QKV projection (only its q block is read here; the caller has already written
+    the row into ``x_cache``); x_cache (B, Lmax, 3HD): the preallocated K/V state of the self part (rows beyond the
+    current step are masked by ``mask_x`` (B or 1, 1, Lmax), so the reference's ``torch.cat`` growth is never needed);
+    h_kv (B, Lh, 2HD): the memory keys / values projected once; mask_h (B or 1, 1, Lh).
+    -> out_x, out_h (B, 1, HD), probs_x (H*B, 1, Lmax), probs_h (H*B, 1, Lh)."""
+    lib = _lib.load()
+    assert q_row.is_contiguous() and x_cache.is_contiguous() and h_kv.is_contiguous()
+    B, _, w = q_row.shape
+    hd = w // 3
+    D = hd // n_head
+    lmax, lh = x_cache.shape[1], h_kv.shape[1]
+    mx, mh = _u8(mask_x), _u8(mask_h)
+    dx = _attn_desc(B, n_head, D, 1, lmax, w, w, w, hd, mx)
+    dh = _attn_desc(B, n_head, D, 1, lh, w, 2 * hd, 2 * hd, hd, mh)
+    out_x = torch.empty(B, 1, hd, device=q_row.device, dtype=torch.float32)
+    out_h = torch.empty_like(out_x)
+    px = torch.empty(n_head * B, 1, lmax, device=q_row.device, dtype=torch.float32)
+    ph = torch.empty(n_head * B, 1, lh, device=q_row.device, dtype=torch.float32)
+    st = stream_ptr()
+    check(lib.kt_attention_fwd(ctypes.byref(dx), _off(q_row, 0), _off(x_cache, hd), _off(x_cache, 2 * hd), ptr(mx), None,
+                               ptr(out_x), ptr(px), None, st), "kt_attention_fwd")
+    check(lib.kt_attention_fwd(ctypes.byref(dh), _off(q_row, 0), _off(h_kv, 0), _off(h_kv, hd), ptr(mh), None,
+                               ptr(out_h), ptr(ph), None, st), "kt_attention_fwd")
+    _count(2)
+    return out_x, out_h, px, ph
+
+
 class FsmnMemoryFn(torch.autograd.Function):
     """MemoryBlockV2 (fsmn.py:46-77).  x (B, T, C), w (C, 1, K), mask (B, T) bool or None."""
 

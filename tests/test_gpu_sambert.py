@@ -286,6 +286,66 @@ def test_sambert_medium_matches_oracle(path):
         assert float(errs.median()) < 1e-2 and float(errs.max()) < 5e-2, (float(errs.median()), float(errs.max()))
 
 
+INFER_KEYS = ("log_duration_predictions", "pitch_predictions", "energy_predictions", "LR_text_outputs", "LR_emo_outputs",
+              "LR_spk_outputs", "dec_outputs", "postnet_outputs")
+
+
+def _infer_model(cfg, sd, inputs, ffma):
+    from kantts_b200 import ops, sambert
+    ops.set_force_ffma(ffma)
+    try:
+        model = sambert.KanTtsSAMBERT(cfg)
+        model.load_state_dict(sd, strict=True)
+        model = model.to(DEV).eval()
+        with torch.no_grad(), torch.backends.cudnn.flags(enabled=False):
+            res = model(inputs["inputs_ling"].to(DEV), inputs["inputs_emotion"].to(DEV), inputs["inputs_speaker"].to(DEV),
+                        inputs["input_lengths"].to(DEV))
+        torch.cuda.synchronize()
+    finally:
+        ops.set_force_ffma(False)
+    return res
+
+
+@pytest.mark.parametrize("path", ["ffma", "tcgen05"])
+def test_sambert_free_running_inference_matches_reference_golden(golden, path):
+    """inference (no targets) -- predicted prosody, autoregressive duration predictor, step-by-step PNCA
+    decoding on a preallocated K/V state -- against the unmodified reference's batch-1 run."""
+    g = golden("sambert_small_infer")
+    res = _infer_model(g.cfg, g.group("sd/"), g.group("in/"), path == "ffma")
+    tol = 2e-5 if path == "ffma" else 2e-4
+    assert torch.equal(res["LR_length_rounded"].cpu(), g.t("out/LR_length_rounded"))
+    assert [res["x_band_width"], res["h_band_width"]] == g.t("out/band_width").tolist()
+    for k in INFER_KEYS:
+        assert res[k].shape == g.t("out/" + k).shape, (k, res[k].shape)
+        assert rel_l2(res[k].cpu(), g.t("out/" + k)) < tol, (k, rel_l2(res[k].cpu(), g.t("out/" + k)))
+    for k in ("pnca_x_attn_lst", "pnca_h_attn_lst"):
+        assert len(res[k]) == g.cfg["decoder_num_layers"]
+        for i, a in enumerate(res[k]):
+            assert rel_l2(a.cpu(), g.t(f"out/{k}.{i}")) < tol, (k, i)
+
+
+def test_sambert_free_running_inference_batch_matches_oracle(golden):
+    """The same on a ragged batch of 3 (the reference cannot: its decoder masks drop the batch dimension) against the
+    CPU oracle's per-item restatement."""
+    from oracle import sambert as osb
+    from golden.make_batch import make_sambert_batch
+    g = golden("sambert_small_infer")
+    batch = make_sambert_batch(g.cfg, B=3, L=9, gen=torch.Generator().manual_seed(31), short=3)
+    inputs = {k: batch[k] for k in ("inputs_ling", "inputs_emotion", "inputs_speaker", "input_lengths")}
+    with torch.no_grad():
+        want = osb.sambert_infer(g.group("sd/"), g.cfg, inputs["inputs_ling"], inputs["inputs_emotion"],
+                                 inputs["inputs_speaker"], inputs["input_lengths"])
+    dur = torch.exp(want["log_duration_predictions"]) - 1
+    frac = (dur + 0.5) - torch.floor(dur + 0.5)
+    assert float(torch.minimum(frac, 1 - frac)[dur > 0].min()) > 2e-3       # no duration sits on a rounding boundary
+    res = _infer_model(g.cfg, g.group("sd/"), inputs, True)
+    assert torch.equal(res["LR_length_rounded"].cpu(), want["LR_length_rounded"])
+    assert res["x_band_width"] == want["x_band_width"]
+    for k in INFER_KEYS:
+        assert res[k].shape == want[k].shape, (k, res[k].shape, want[k].shape)
+        assert rel_l2(res[k].cpu(), want[k]) < 2e-5, (k, rel_l2(res[k].cpu(), want[k]))
+
+
 def test_sambert_c4_train_step_runs_and_learns():
     """BASELINE configs[3] shape (batch 32, 256 symbols, 768 mel frames, 80 mels), train() mode with the yaml's
     dropouts, through SambertStep: losses finite, parameters move, the loss goes down over a few steps."""
