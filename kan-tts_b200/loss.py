@@ -13,68 +13,57 @@ from . import ops
 from .audio import MelSpectrogram, stft
 
 
-class GeneratorAdversarialLoss(torch.nn.Module):
+def _as_list(outputs):
+    """The trainer hands over one tensor per sub-discriminator (a list / tuple); a bare tensor counts as one."""
+    return list(outputs) if isinstance(outputs, (tuple, list)) else [outputs]
+
+
+def _last(o):
+    """A sub-discriminator result may itself be a (feature maps ..., logits) sequence: the logits come last."""
+    return o[-1] if isinstance(o, (tuple, list)) else o
+
+
+def _gan_term(logits, target, loss_type):
+    """One sub-discriminator's contribution.  mse: LSGAN distance to ``target`` (1 = real, 0 = fake);
+    hinge: mean of min(sign * logits - 1, 0) negated, sign = +1 for the real side, -1 for the fake side."""
+    if loss_type == "mse":
+        return torch.mean((logits - target) ** 2)
+    sign = 1.0 if target > 0.5 else -1.0
+    return -torch.mean(torch.clamp(sign * logits - 1.0, max=0.0))
+
+
+class _AdversarialBase(torch.nn.Module):
     def __init__(self, average_by_discriminators=True, loss_type="mse"):
         super().__init__()
-        self.average_by_discriminators = average_by_discriminators
         assert loss_type in ["mse", "hinge"], f"{loss_type} is not supported."
-        self.criterion = self._mse_loss if loss_type == "mse" else self._hinge_loss
+        self.average_by_discriminators = average_by_discriminators
+        self.loss_type = loss_type
+
+    def _reduce(self, terms):
+        total = sum(terms[1:], terms[0])
+        return total / len(terms) if self.average_by_discriminators and len(terms) > 1 else total
+
+
+class GeneratorAdversarialLoss(_AdversarialBase):
+    """kantts/train/loss.py:108-145: the generator wants every sub-discriminator to call its output real
+    (mse: distance to 1; hinge: -mean(logits)); summed over the sub-discriminators, optionally averaged."""
 
     def forward(self, outputs):
-        if isinstance(outputs, (tuple, list)):
-            adv_loss = 0.0
-            for i, outputs_ in enumerate(outputs):
-                adv_loss += self.criterion(outputs_)
-            if self.average_by_discriminators:
-                adv_loss /= i + 1
+        if self.loss_type == "mse":
+            terms = [_gan_term(o, 1.0, "mse") for o in _as_list(outputs)]
         else:
-            adv_loss = self.criterion(outputs)
-        return adv_loss
-
-    def _mse_loss(self, x):
-        return F.mse_loss(x, x.new_ones(x.size()))
-
-    def _hinge_loss(self, x):
-        return -x.mean()
+            terms = [-torch.mean(o) for o in _as_list(outputs)]
+        return self._reduce(terms)
 
 
-class DiscriminatorAdversarialLoss(torch.nn.Module):
-    def __init__(self, average_by_discriminators=True, loss_type="mse"):
-        super().__init__()
-        self.average_by_discriminators = average_by_discriminators
-        assert loss_type in ["mse", "hinge"], f"{loss_type} is not supported."
-        if loss_type == "mse":
-            self.fake_criterion, self.real_criterion = self._mse_fake_loss, self._mse_real_loss
-        else:
-            self.fake_criterion, self.real_criterion = self._hinge_fake_loss, self._hinge_real_loss
+class DiscriminatorAdversarialLoss(_AdversarialBase):
+    """kantts/train/loss.py:148-214: (real_loss, fake_loss) -- real outputs pushed to 1, generated ones to 0
+    (mse) or past the +-1 margins (hinge)."""
 
     def forward(self, outputs_hat, outputs):
-        if isinstance(outputs, (tuple, list)):
-            real_loss, fake_loss = 0.0, 0.0
-            for i, (outputs_hat_, outputs_) in enumerate(zip(outputs_hat, outputs)):
-                if isinstance(outputs_hat_, (tuple, list)):
-                    outputs_hat_, outputs_ = outputs_hat_[-1], outputs_[-1]
-                real_loss += self.real_criterion(outputs_)
-                fake_loss += self.fake_criterion(outputs_hat_)
-            if self.average_by_discriminators:
-                fake_loss /= i + 1
-                real_loss /= i + 1
-        else:
-            real_loss = self.real_criterion(outputs)
-            fake_loss = self.fake_criterion(outputs_hat)
-        return real_loss, fake_loss
-
-    def _mse_real_loss(self, x):
-        return F.mse_loss(x, x.new_ones(x.size()))
-
-    def _mse_fake_loss(self, x):
-        return F.mse_loss(x, x.new_zeros(x.size()))
-
-    def _hinge_real_loss(self, x):
-        return -torch.mean(torch.min(x - 1, x.new_zeros(x.size())))
-
-    def _hinge_fake_loss(self, x):
-        return -torch.mean(torch.min(-x - 1, x.new_zeros(x.size())))
+        fake = [_gan_term(_last(o), 0.0, self.loss_type) for o in _as_list(outputs_hat)]
+        real = [_gan_term(_last(o), 1.0, self.loss_type) for o in _as_list(outputs)]
+        return self._reduce(real), self._reduce(fake)
 
 
 def _l1_mean(a, b):
@@ -92,26 +81,27 @@ def _l1_mean(a, b):
 
 
 class FeatureMatchLoss(torch.nn.Module):
+    """kantts/train/loss.py:217-256: sum over sub-discriminators of the (summed or averaged) per-layer L1 distance
+    between two feature-map pyramids; the second argument is treated as a constant."""
+
     def __init__(self, average_by_layers=True, average_by_discriminators=True):
         super().__init__()
         self.average_by_layers = average_by_layers
         self.average_by_discriminators = average_by_discriminators
 
     def forward(self, feats_hat, feats):
-        feat_match_loss = 0.0
-        for i, (feats_hat_, feats_) in enumerate(zip(feats_hat, feats)):
-            feat_match_loss_ = 0.0
-            for j, (feat_hat_, feat_) in enumerate(zip(feats_hat_, feats_)):
-                feat_match_loss_ += _l1_mean(feat_hat_, feat_)
-            if self.average_by_layers:
-                feat_match_loss_ /= j + 1
-            feat_match_loss += feat_match_loss_
-        if self.average_by_discriminators:
-            feat_match_loss /= i + 1
-        return feat_match_loss
+        per_disc = []
+        for maps_hat, maps in zip(feats_hat, feats):
+            layer_terms = [_l1_mean(a, b) for a, b in zip(maps_hat, maps)]
+            value = sum(layer_terms[1:], layer_terms[0])
+            per_disc.append(value / len(layer_terms) if self.average_by_layers else value)
+        total = sum(per_disc[1:], per_disc[0])
+        return total / len(per_disc) if self.average_by_discriminators else total
 
 
 class MelSpectrogramLoss(torch.nn.Module):
+    """kantts/train/loss.py:259-311: L1 between the normalised log-mel spectrograms (fused STFT-mel kernel)."""
+
     def __init__(self, fs=22050, fft_size=1024, hop_size=256, win_length=None, window="hann", num_mels=80,
                  fmin=80, fmax=7600, center=True, normalized=False, onesided=True, eps=1e-10, log_base=10.0):
         super().__init__()
@@ -121,22 +111,26 @@ class MelSpectrogramLoss(torch.nn.Module):
                                               log_base=log_base)
 
     def forward(self, y_hat, y):
-        mel_hat = self.mel_spectrogram(y_hat)
-        mel = self.mel_spectrogram(y)
-        return F.l1_loss(mel_hat, mel)
+        return torch.mean(torch.abs(self.mel_spectrogram(y_hat) - self.mel_spectrogram(y)))
 
 
 class SpectralConvergenceLoss(torch.nn.Module):
+    """kantts/train/loss.py:314-331: || |Y| - |X| ||_F / || |Y| ||_F."""
+
     def forward(self, x_mag, y_mag):
-        return torch.norm(y_mag - x_mag, p="fro") / torch.norm(y_mag, p="fro")
+        return torch.linalg.vector_norm(y_mag - x_mag) / torch.linalg.vector_norm(y_mag)
 
 
 class LogSTFTMagnitudeLoss(torch.nn.Module):
+    """kantts/train/loss.py:334-350: L1 between the log magnitudes."""
+
     def forward(self, x_mag, y_mag):
-        return F.l1_loss(torch.log(y_mag), torch.log(x_mag))
+        return torch.mean(torch.abs(torch.log(y_mag) - torch.log(x_mag)))
 
 
 class STFTLoss(torch.nn.Module):
+    """kantts/train/loss.py:353-389: one resolution -> (spectral convergence, log-magnitude L1)."""
+
     def __init__(self, fft_size=1024, shift_size=120, win_length=600, window="hann_window"):
         super().__init__()
         self.fft_size, self.shift_size, self.win_length = fft_size, shift_size, win_length
@@ -145,30 +139,27 @@ class STFTLoss(torch.nn.Module):
         self.register_buffer("window", getattr(torch, window)(win_length))
 
     def forward(self, x, y):
-        x_mag = stft(x, self.fft_size, self.shift_size, self.win_length, self.window)
-        y_mag = stft(y, self.fft_size, self.shift_size, self.win_length, self.window)
-        return self.spectral_convergence_loss(x_mag, y_mag), self.log_stft_magnitude_loss(x_mag, y_mag)
+        mags = [stft(w, self.fft_size, self.shift_size, self.win_length, self.window) for w in (x, y)]
+        return self.spectral_convergence_loss(*mags), self.log_stft_magnitude_loss(*mags)
 
 
 class MultiResolutionSTFTLoss(torch.nn.Module):
+    """kantts/train/loss.py:392-441: mean over the resolutions of both STFT loss terms; (B, bands, T) inputs
+    (sub-band signals) are folded into the batch."""
+
     def __init__(self, fft_sizes=[1024, 2048, 512], hop_sizes=[120, 240, 50], win_lengths=[600, 1200, 240],
                  window="hann_window"):
         super().__init__()
         assert len(fft_sizes) == len(hop_sizes) == len(win_lengths)
-        self.stft_losses = torch.nn.ModuleList()
-        for fs, ss, wl in zip(fft_sizes, hop_sizes, win_lengths):
-            self.stft_losses += [STFTLoss(fs, ss, wl, window)]
+        self.stft_losses = torch.nn.ModuleList(
+            [STFTLoss(*cfg, window) for cfg in zip(fft_sizes, hop_sizes, win_lengths)])
 
     def forward(self, x, y):
-        if len(x.shape) == 3:
-            x = x.view(-1, x.size(2))
-            y = y.view(-1, y.size(2))
-        sc_loss, mag_loss = 0.0, 0.0
-        for f in self.stft_losses:
-            sc_l, mag_l = f(x, y)
-            sc_loss += sc_l
-            mag_loss += mag_l
-        return sc_loss / len(self.stft_losses), mag_loss / len(self.stft_losses)
+        if x.dim() == 3:
+            x, y = x.reshape(-1, x.size(2)), y.reshape(-1, y.size(2))
+        terms = [f(x, y) for f in self.stft_losses]
+        n = len(terms)
+        return sum(t[0] for t in terms) / n, sum(t[1] for t in terms) / n
 
 
 loss_dict = {
