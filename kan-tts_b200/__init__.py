@@ -7,18 +7,20 @@ Public surface = the reference's own module API for this path:
   train.GanStep (GAN_Trainer.train_step + the data-parallel gradient exchange)
   sambert.KanTtsSAMBERT + MelReconLoss / ProsodyReconLoss                  (kantts.models.sambert, kantts.train.loss)
   train.SambertStep (Sambert_Trainer.train_step)
+  infer.synthesize (symbols -> SAM-BERT free-running decode -> HiFi-GAN -> waveforms, no .npy hand-off)
   install.install() patches these into an importable KAN-TTS checkout.
 All tensor math runs in libkantts_b200.so (C ABI: include/kantts_b200.h); there is no fallback.
 """
 from . import _lib  # noqa: F401
 from ._lib import build_library  # noqa: F401
-from . import ops, hifigan, audio, loss, sambert_ops, sambert, train, install as _install  # noqa: F401
+from . import ops, hifigan, audio, loss, sambert_ops, sambert, train, infer, install as _install  # noqa: F401
 from .sambert import KanTtsSAMBERT, MelReconLoss, ProsodyReconLoss  # noqa: F401
 from .hifigan import Generator, MultiPeriodDiscriminator, MultiScaleDiscriminator  # noqa: F401
 from .audio import MelSpectrogram, stft  # noqa: F401
 from .loss import (MelSpectrogramLoss, MultiResolutionSTFTLoss, GeneratorAdversarialLoss,  # noqa: F401
                    DiscriminatorAdversarialLoss, FeatureMatchLoss, criterion_builder)
 from .train import GanStep, SambertStep, hifigan_model_builder, sambert_model_builder  # noqa: F401
+from .infer import synthesize  # noqa: F401
 
 
 
