@@ -1,6 +1,6 @@
-"""Per-tensor gradient error of the full-width SAM-BERT on the short ragged batch, both compute paths."""
+"""(test tooling: it calls the oracle, so it lives under tests/)  Per-tensor gradient error of the full-width SAM-BERT on the short ragged batch, both compute paths."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in tests/)
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import kantts_b200
