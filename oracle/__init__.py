@@ -2,8 +2,10 @@
 
 A CPU restatement (plain PyTorch-CPU / numpy, fp32 unless noted) of the one
 KAN-TTS hot path this repo accelerates: HiFi-GAN Generator / MultiPeriod- /
-MultiScale-Discriminator, the mel-spectrogram / STFT losses, the LSGAN losses
-and the GAN train-step schedule.  Every function cites the reference file:line
+MultiScale-Discriminator (incl. the neural-source-filter generator variant), the
+mel-spectrogram / STFT losses, the LSGAN losses and the GAN train-step schedule;
+the SAM-BERT acoustic model (teacher-forced training step and free-running
+inference) in oracle/sambert.py.  Every function cites the reference file:line
 it restates (paths relative to the KAN-TTS checkout, /root/reference).
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /

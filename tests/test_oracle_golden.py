@@ -125,3 +125,15 @@ def test_mel_basis_matches_torchaudio():
         ours = melbasis.mel_filterbank(sr, n_fft, n_mels, fmin, fmax)
         ref = ta.functional.melscale_fbanks(n_fft // 2 + 1, fmin, fmax, n_mels, sr, norm="slaney", mel_scale="slaney").T.numpy()
         assert np.abs(ours - ref).max() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["gen_small_nsf_causal", "gen_small_nsf_noncausal"])
+def test_nsf_generator_matches_reference(golden, name):
+    """the neural-source-filter generator variant (sine + noise excitation, per-stage strided
+    ``source_downs``), same RNG seed -> same random phases / noise as the reference run."""
+    g = golden(name)
+    with torch.no_grad():
+        torch.manual_seed(int(g.arrays["rng_seed"]))
+        y = O.generator_forward(g.group("sd/"), g.t("x"), **g.cfg)
+    assert y.shape == g.t("y").shape
+    assert float((y - g.t("y")).abs().max()) < 2e-6
