@@ -9,12 +9,14 @@ leaf ``nn.Parameter``s so ``torch.optim.Adam`` / ``DistributedDataParallel`` wor
 Every tensor op of the forward and backward runs in libkantts_b200.so (hand-written sm_100a
 kernels) through ``ops.py``; activations are channels-last rows internally and are converted only
 at the module boundary (feature maps are returned as zero-copy permuted views).
-Out of scope: NSF source module, MultiSpecDiscriminator, PQMF.
+The NSF branch (``nsf_params``) is module plumbing over the same kernels and has NOT run on a GPU yet (round 1 ran out
+of GPU budget: tests/test_gpu_pipeline.py is opt-in).  Out of scope: MultiSpecDiscriminator, PQMF.
 """
 import copy
 import math
 import os
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -264,6 +266,51 @@ class ResidualBlock(nn.Module):
             layer.remove_weight_norm()
 
 
+class SourceModule(nn.Module):
+    """layers.py:229-290: sine-plus-noise excitation of the neural source filter + a weight-normed 1x1 conv
+    (nb_harmonics + 1 -> 1) + tanh (fused into the conv's epilogue).  The excitation itself is O(samples x 8)
+    elementwise work under ``no_grad``; like the reference, the random initial phases and the noise are drawn on the
+    HOST from torch's global CPU generator (``Uniform`` / ``Normal`` with Python-float parameters sample on the CPU,
+    layers.py:266-279) and copied over, which keeps the RNG stream identical to the reference's."""
+
+    def __init__(self, nb_harmonics, upsample_ratio, sampling_rate, alpha=0.1, sigma=0.003):
+        super().__init__()
+        self.nb_harmonics, self.upsample_ratio, self.sampling_rate = nb_harmonics, int(upsample_ratio), sampling_rate
+        self.alpha, self.sigma = alpha, sigma
+        ref = nn.Conv1d(nb_harmonics + 1, 1, kernel_size=1, stride=1)
+        spec = ops.ConvSpec(c_in=nb_harmonics + 1, c_out=1, kernel=1)
+        spec.act_out = KT_ACT_TANH
+        self.ffn = nn.Sequential(_NormedConv(ref, spec, "weight"), nn.Tanh())    # keys ffn.0.{bias,weight_g,weight_v}
+
+    def excitation(self, pitch, uv):
+        """(B, 1, frames) pitch in Hz and voiced flag -> (B, samples, nb_harmonics + 1) rows (no gradient)."""
+        from torch.distributions.normal import Normal
+        from torch.distributions.uniform import Uniform
+        with torch.no_grad():
+            pitch_s = F.interpolate(pitch, scale_factor=self.upsample_ratio, mode="nearest")
+            uv_s = F.interpolate(uv, scale_factor=self.upsample_ratio, mode="nearest")
+            harm = torch.arange(1, self.nb_harmonics + 2, device=pitch.device, dtype=pitch_s.dtype)[None, :, None]
+            theta = 2 * math.pi * (torch.cumsum(pitch_s * harm / self.sampling_rate, dim=-1) % 1)
+            phase = Uniform(low=-math.pi, high=math.pi).sample(sample_shape=(pitch.size(0), self.nb_harmonics + 1, 1))
+            phase[:, 0, :] = 0
+            noise = Normal(loc=0.0, scale=self.sigma).sample(
+                sample_shape=(pitch_s.size(0), self.nb_harmonics + 1, pitch_s.size(-1)))
+            phase, noise = phase.to(pitch.device), noise.to(pitch.device)
+            e_voice = self.alpha * torch.sin(theta + phase) + noise
+            e_unvoice = self.alpha / 3 / self.sigma * noise
+            e = e_voice * uv_s + e_unvoice * (1 - uv_s)
+            return e.transpose(1, 2).contiguous()
+
+    def forward_rows(self, pitch, uv):
+        return self.ffn[0].run(self.excitation(pitch, uv))          # (B, samples, 1)
+
+    def forward(self, pitch, uv):
+        return self.forward_rows(pitch, uv).transpose(1, 2)
+
+    def remove_weight_norm(self):
+        self.ffn[0].remove_weight_norm()
+
+
 # --------------------------------------------------------------------------------------------
 # Generator (hifigan.py:22-198)
 # --------------------------------------------------------------------------------------------
@@ -279,8 +326,6 @@ class Generator(nn.Module):
         assert kernel_size % 2 == 1, "Kernal size must be odd number."
         assert len(upsample_scales) == len(upsample_kernal_sizes)
         assert len(resblock_dilations) == len(resblock_kernel_sizes)
-        if nsf_params is not None:
-            raise NotImplementedError("kantts_b200: NSF source module is out of scope (SURVEY.md 8a)")
         if not repeat_upsample:
             raise NotImplementedError("kantts_b200: repeat_upsample=False is not used by any shipped config")
         if nonlinear_activation != "LeakyReLU":
@@ -293,7 +338,7 @@ class Generator(nn.Module):
         self.num_upsamples = len(upsample_kernal_sizes)
         self.num_kernels = len(resblock_kernel_sizes)
         self.out_channels = out_channels
-        self.nsf_enable = False
+        self.nsf_enable = nsf_params is not None
         if self.num_kernels > 3:
             raise NotImplementedError("kantts_b200: at most 3 parallel resblocks per stage")
 
@@ -327,12 +372,29 @@ class Generator(nn.Module):
         self.conv_post = conv_cls(channels // (2 ** (i + 1)), out_channels, kernel_size, 1,
                                   padding=(kernel_size - 1) // 2, act_in=0.01)
         self.conv_post.conv1d.spec.act_out = KT_ACT_TANH
+        if self.nsf_enable:
+            # hifigan.py:119-143: the excitation at the sample rate, brought down to every stage's rate by a strided
+            # conv (kernel 2u, stride u, padding u//2; the full-rate stage uses a plain 1x1 conv)
+            self.source_module = SourceModule(nb_harmonics=nsf_params["nb_harmonics"],
+                                              upsample_ratio=int(np.cumprod(list(upsample_scales))[-1]),
+                                              sampling_rate=nsf_params["sampling_rate"])
+            self.source_downs = nn.ModuleList()
+            self.downsample_rates = [1] + list(upsample_scales)[::-1][:-1]
+            self.downsample_cum_rates = np.cumprod(self.downsample_rates)
+            for i, u in enumerate(self.downsample_cum_rates[::-1]):
+                u = int(u)
+                if u == 1:
+                    self.source_downs.append(Conv1d(1, channels // (2 ** (i + 1)), 1, 1))
+                else:
+                    self.source_downs.append(conv_cls(1, channels // (2 ** (i + 1)), u * 2, u, padding=u // 2))
 
-    def forward_rows(self, x):
+    def forward_rows(self, x, excitation=None):
         x = self.conv_pre.forward_rows(x)
         for i in range(self.num_upsamples):
             x = ops.SinAddFn.apply(x)                                        # hifigan.py:157
             rep = self.repeat_upsamples[i][2].forward_rows(x)                # :158
+            if excitation is not None:                                       # :162-166  x = rep + e + up (adds fused)
+                rep = self.source_downs[i].forward_rows(excitation, resid=rep)
             x = self.transpose_upsamples[i][1].forward_rows(x, resid=rep)    # :160,168 (crop fused: t_out)
             par = x.is_cuda and _PARALLEL_STREAMS and self.num_kernels > 1
             if par:                                                           # the parallel resblocks are independent
@@ -352,8 +414,13 @@ class Generator(nn.Module):
         return self.conv_post.forward_rows(x)                                # :178-180
 
     def forward(self, x):
-        """x: (B, in_channels, T) -> (B, 1, T * prod(scales))"""
-        y = self.forward_rows(x.transpose(1, 2).contiguous())               # (B, T', 1)
+        """x: (B, in_channels, T) -> (B, 1, T * prod(scales)); with ``nsf_params`` the last two channels are the
+        pitch (Hz) and the voiced flag (hifigan.py:146-150)."""
+        excitation = None
+        if self.nsf_enable:
+            x, pitch, uv = x[:, :-2, :], x[:, -2:-1, :], x[:, -1:, :]
+            excitation = self.source_module.forward_rows(pitch, uv)         # (B, samples, 1)
+        y = self.forward_rows(x.transpose(1, 2).contiguous(), excitation)   # (B, T', 1)
         return y.transpose(1, 2)
 
     def remove_weight_norm(self):
@@ -366,6 +433,10 @@ class Generator(nn.Module):
             layer.remove_weight_norm()
         self.conv_pre.remove_weight_norm()
         self.conv_post.remove_weight_norm()
+        if self.nsf_enable:                                   # (the reference forgets these; harmless either way)
+            self.source_module.remove_weight_norm()
+            for layer in self.source_downs:
+                layer.remove_weight_norm()
 
 
 # --------------------------------------------------------------------------------------------

@@ -49,3 +49,25 @@ def test_synthesize_matches_oracle_composition(golden):
         assert w.shape == (n,)
         assert float((w.cpu() - wav_o[b, 0, :n]).pow(2).mean().sqrt()) < 1e-3      # waveform RMS tolerance
         assert rel_l2(w.cpu(), wav_o[b, 0, :n]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["gen_small_nsf_causal", "gen_small_nsf_noncausal"])
+def test_nsf_generator_matches_reference_golden(golden, name):
+    """Generator(nsf_params=...) -- source module + per-stage source_downs -- against the unmodified
+    reference's output (same RNG seed: the excitation's random phases / noise are drawn on the host like the reference)."""
+    import kantts_b200 as K
+    from kantts_b200 import ops
+    g = golden(name)
+    m = K.Generator(**g.cfg)
+    m.load_state_dict(g.group("sd/"), strict=True)
+    m = m.to("cuda").eval()
+    for force in (True, False):
+        ops.set_force_ffma(force)
+        try:
+            with torch.no_grad():
+                torch.manual_seed(int(g.arrays["rng_seed"]))
+                y = m(g.t("x").to("cuda")).cpu()
+        finally:
+            ops.set_force_ffma(False)
+        assert y.shape == g.t("y").shape
+        assert float((y - g.t("y")).pow(2).mean().sqrt()) < (1e-5 if force else 1e-3), (force,)
