@@ -136,13 +136,26 @@ def check(rc, what):
         raise RuntimeError(f"{what} failed (code {rc}): {msg}")
 
 
-def ptr(t):
-    """device pointer of a tensor (None -> NULL); the tensor must be CUDA, fp32, contiguous."""
+_PTR_DTYPES = (torch.float32,)
+_AUX_DTYPES = (torch.uint8, torch.int32, torch.bfloat16)   # masks / keep-masks, gather indices, packed tcgen05 weight tiles
+
+
+def ptr(t, aux=False):
+    """device pointer of a tensor (None -> NULL).  The tensor must be contiguous fp32 on the CURRENT CUDA device (the
+    kernels are launched on the current device's stream and read raw fp32); ``aux=True`` admits the integer / byte /
+    packed-bf16 side arguments of the ABI (masks, indices, weight tile images).  A float64 / half tensor here would be
+    silently reinterpreted (or read out of bounds), so it is an error -- cast at the module boundary."""
     if t is None:
         return None
     if not (t.is_cuda and t.is_contiguous()):
         raise RuntimeError(f"kantts_b200: expected a contiguous CUDA tensor, got device={t.device} "
                            f"contiguous={t.is_contiguous()} (no CPU fallback)")
+    if t.dtype not in _PTR_DTYPES and not (aux and t.dtype in _AUX_DTYPES):
+        raise RuntimeError(f"kantts_b200: expected a float32 tensor, got {t.dtype} (cast at the module boundary; the "
+                           "kernels read raw fp32)")
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"kantts_b200: tensor on {t.device} but the current device is cuda:{torch.cuda.current_device()} "
+                           "(wrap the call in torch.cuda.device(...))")
     return t.data_ptr()
 
 

@@ -160,6 +160,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   uint64_t* tmem_full = empty_b + p.nb_stages;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  // per-tap image row shift in descriptor units (16 bytes): the MMA issuer reads it with one LDS per tap instead of a
+  // dynamically indexed kernel-parameter load (constant-bank miss + address arithmetic on the issuing thread)
+  uint32_t* s_tapshift = tmem_slot + 4;          // [kMaxTaps]
+  float* epi_stage = reinterpret_cast<float*>(s_tapshift + kMaxTaps);   // 4 epilogue warps x (32 rows x 32 fp32), 16-byte aligned
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mtiles = p.ph_mt0[p.nphases];   // m-tiles of all phases (each: 128 flattened outputs m * nsub + w)
@@ -173,6 +177,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     fence_proxy_async();
   }
   if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (tid >= 192 && tid < 192 + kMaxTaps) s_tapshift[tid - 192] = (uint32_t)p.tap_shift[tid - 192] * 8u;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -245,9 +250,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     __syncwarp();
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
+    // One elected thread.  Everything it touches per MMA is a 32-bit add: the UMMA shared-memory descriptors are kept as
+    // (lo word, constant hi word) pairs -- lo = (address >> 4) | LBO field, so a tap's row shift, the K = 16 slice offset
+    // (32 bytes = 2 units) and the hi -> lo plane distance are plain integer adds on the lo word (shared-memory addresses
+    // are < 2^18, so the 14-bit address field never carries into the LBO field).  Resident weight slots are waited for
+    // once per CTA (their single phase completes once and stays complete); ring stages once per (chunk, tap).
     if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(kTcM, p.NT, 0, 0);
       const uint32_t idesc2 = make_idesc_bf16(kTcM, 2 * p.NT, 0, 0);
+      const uint32_t a_base16 = (smem_u32(a_base) >> 4) | 0x10000u;     // descriptor lo word of stage 0, hi plane
+      const uint32_t b_base16 = (smem_u32(b_base) >> 4) | 0x10000u;
+      const uint32_t a_stage16 = (uint32_t)a_stage_bytes >> 4, img16 = (uint32_t)img_bytes >> 4;
+      const uint32_t b_stage16 = (uint32_t)b_stage_bytes >> 4, bplane16 = (uint32_t)(p.NT * 128) >> 4;
+      const bool resident = p.w_resident != 0, fuse2 = p.fuse2 != 0;
       int it_a = 0, it_b = 0, ti = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
         const int buf = ti & 1;
@@ -259,46 +274,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         uint32_t acc = 0;
         int ph = 0;
         while ((tile % mtiles) >= p.ph_mt0[ph + 1]) ++ph;
+        const int g_begin = p.ph_g0[ph], g_end = p.ph_g0[ph + 1];
         for (int c = 0; c < p.kchunks; ++c) {
           const int kslices = (min(kTcKC, p.kg - c * kTcKC) + 15) >> 4;   // K = 16 slices holding real channels
-          for (int g = p.ph_g0[ph]; g < p.ph_g0[ph + 1]; ++g, ++it_a) {
+          for (int g = g_begin; g < g_end; ++g, ++it_a) {
             const int sa = it_a % p.na_stages;
             // (no tcgen05.fence here or after the weight wait: the producers' fence.proxy.async + mbarrier release
-            //  / the bulk copy's complete_tx make the data visible to the MMA's async-proxy reads; a
-            //  fence::after_thread_sync per tap drained the MMA pipeline -- the MMA phase was ~constant per TAP,
-            //  not per instruction, profiles/r01_notes.md)
+            //  / the bulk copy's complete_tx make the data visible to the MMA's async-proxy reads)
             mbar_wait(&full_a[sa], (it_a / p.na_stages) & 1);
-            if (c == 0 && g == p.ph_g0[ph]) trace_ev(p, 2, ti, 2);
-            const uint32_t a_hi = smem_u32(a_base + (size_t)sa * a_stage_bytes);
-            const uint32_t a_lo = a_hi + (uint32_t)img_bytes;
-            for (int n = p.grp_first[g]; n < p.grp_first[g + 1]; ++n, ++it_b) {
-              const int sb = p.w_resident ? c * p.ntaps + n : it_b % p.nb_stages;
-              // (resident slots complete their single phase 0 once and stay complete)
-              if (ti == 1 && c == 0) trace_ev(p, 4, n & 15, 0);     // role 4: per-tap stamps of the MMA issuer, tile 1
-              mbar_wait(&full_b[sb], p.w_resident ? 0u : (uint32_t)((it_b / p.nb_stages) & 1));
-              if (ti == 1 && c == 0) trace_ev(p, 4, n & 15, 1);
-              const uint32_t b_hi = smem_u32(b_base + (size_t)sb * b_stage_bytes);
-              const uint32_t b_lo = b_hi + (uint32_t)(p.NT * 128);
-              const uint32_t shift = (uint32_t)p.tap_shift[n] * 128u;
-              for (int kk = 0; kk < kslices; ++kk) {
-                const uint32_t ko = (uint32_t)kk * 32u;
-                const uint64_t da_hi = smem_desc_sw128(a_hi + shift + ko, 16, 1024, false);
-                const uint64_t da_lo = smem_desc_sw128(a_lo + shift + ko, 16, 1024, false);
-                const uint64_t db_hi = smem_desc_sw128(b_hi + ko, 16, 1024, false);
-                const uint64_t db_lo = smem_desc_sw128(b_lo + ko, 16, 1024, false);
-                if (p.fuse2) {
-                  umma_bf16(d_tmem, da_hi, db_hi, idesc2, acc);     // [a_hi*b_hi | a_hi*b_lo] -> columns [0, 2*NT)
-                  umma_bf16(d_tmem, da_lo, db_hi, idesc, 1);        //  a_lo*b_hi             -> columns [0, NT)
-                } else {
-                  umma_bf16(d_tmem, da_lo, db_hi, idesc, acc);
-                  umma_bf16(d_tmem, da_hi, db_lo, idesc, 1);
-                  umma_bf16(d_tmem, da_hi, db_hi, idesc, 1);
-                }
-                acc = 1;
+            if (c == 0 && g == g_begin) trace_ev(p, 2, ti, 2);
+            const uint32_t a16 = a_base16 + (uint32_t)sa * a_stage16;
+            const int n_begin = p.grp_first[g], n_end = p.grp_first[g + 1];
+            uint32_t sh = s_tapshift[n_begin];
+            for (int n = n_begin; n < n_end; ++n, ++it_b) {
+              const uint32_t a_hi = a16 + sh;
+              if (n + 1 < n_end) sh = s_tapshift[n + 1];          // next tap's shift: its LDS latency hides behind this tap's MMAs
+              int sb;
+              if (resident) {
+                sb = c * p.ntaps + n;
+                if (ti == 0) mbar_wait(&full_b[sb], 0u);
+              } else {
+                sb = it_b % p.nb_stages;
+                mbar_wait(&full_b[sb], (uint32_t)((it_b / p.nb_stages) & 1));
               }
-              if (ti == 1 && c == 0) trace_ev(p, 4, n & 15, 2);
-              if (!p.w_resident) umma_commit(&empty_b[sb]);
-              if (ti == 1 && c == 0) trace_ev(p, 4, n & 15, 3);
+              const uint32_t b_hi = b_base16 + (uint32_t)sb * b_stage16;
+              if (fuse2) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  if (kk < kslices) {
+                    umma_bf16_lo(d_tmem, a_hi + 2u * kk, b_hi + 2u * kk, idesc2, acc);       // [a_hi*b_hi | a_hi*b_lo] -> columns [0, 2*NT)
+                    umma_bf16_lo(d_tmem, a_hi + img16 + 2u * kk, b_hi + 2u * kk, idesc, 1u);  //  a_lo*b_hi             -> columns [0, NT)
+                    acc = 1;
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  if (kk < kslices) {
+                    umma_bf16_lo(d_tmem, a_hi + img16 + 2u * kk, b_hi + 2u * kk, idesc, acc);
+                    umma_bf16_lo(d_tmem, a_hi + 2u * kk, b_hi + bplane16 + 2u * kk, idesc, 1u);
+                    umma_bf16_lo(d_tmem, a_hi + 2u * kk, b_hi + 2u * kk, idesc, 1u);
+                    acc = 1;
+                  }
+                }
+              }
+              if (!resident) umma_commit(&empty_b[sb]);
             }
             umma_commit(&empty_a[sa]);
           }
@@ -310,7 +330,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     __syncwarp();
   } else {
     // ===================== epilogue (warps 6-9; TMEM lane quarter = warp & 3) =====================
+    // tcgen05.ld hands every thread ONE output row (32 fp32 columns per chunk).  Writing rows straight from that layout
+    // makes each 16-byte warp store touch 32 different 128-byte lines (measured: 9 us to drain one 128 x 128 tile, ~2
+    // cycles per line -- LSU-bound, profiles/r02_notes.md).  Instead every warp transposes its 32 x 32 chunk through a
+    // private 4 KB shared-memory tile (16-byte chunks XOR-swizzled by row: conflict-free both ways) so that 8 consecutive
+    // lanes cover one 128-byte row segment: residual / mask loads, the read-modify-write of `accumulate` and the stores
+    // are all fully coalesced (4 lines per warp instruction).  Bias and the output activation are applied before the
+    // transposition (they are per column), residual / derivative masks after it (they are per element).
     const int quarter = warp & 3;
+    float* stg = epi_stage + (size_t)quarter * (32 * 32);
     int ti = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       const int gm = tile % mtiles, nt = (tile / mtiles) % p.ntiles, bb = tile / (mtiles * p.ntiles);
@@ -335,9 +363,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       // forward: residual add; data gradient: act_in' mask -- never both (the scalar path handles the general case)
       const float* side_p = p.resid ? p.resid : p.mask.p;
       const bool side_is_mask = p.resid == nullptr;
-      const bool batched = valid && vec_out && !(p.resid && p.mask.p);
+      const bool coalesced = vec_out && !(p.resid && p.mask.p);          // warp-uniform
+      // rows this lane serves in the coalesced phase: row_i = 4 * i + lane / 8 (i = 0..7), 16-byte chunk lane % 8
+      long long rbase[8];
+      uint32_t rok = 0;
+      if (coalesced) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int src = i * 4 + (lane >> 3);
+          rbase[i] = __shfl_sync(0xffffffffu, obase, src);
+          rok |= (uint32_t)__shfl_sync(0xffffffffu, (int)valid, src) << i;
+        }
+      }
       for (int n0 = 0; n0 < p.NT; n0 += 32) {
         uint32_t rr[32];
+        if (tid == 192 && ti < 2) trace_ev(p, 4 + ti, n0 >> 5, 0);   // roles 4 / 5: per-chunk stamps of epilogue warp 0, tiles 0 / 1
         if (p.NT - n0 >= 32) {
           tmem_ld32(t_lane + (uint32_t)n0, rr);
         } else {  // NT % 32 == 16
@@ -346,14 +386,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int e = 0; e < 16; ++e) { rr[e] = r16[e]; rr[16 + e] = 0u; }
         }
-        // all side-tensor loads of this 32-column chunk are issued back to back (and before the TMEM load is
-        // waited for): a load -> add -> store chain per 16 bytes cost ~0.5 us x 8 per chunk (profiles/r02_tc_trace.md)
-        const int ncols = valid ? min(32, n_valid - n0) : 0;
+        const int ncols_t = min(32, n_valid - n0);       // real columns of this chunk (tile-uniform, may be <= 0)
+        // side-tensor loads are issued before the TMEM load is waited for (coalesced: this lane's 8 (row, chunk) cells)
+        const int cq = lane & 7;
+        const bool col_ok = cq * 4 < ncols_t;
         float4 sd[8];
-        if (batched && side_p) {
+        if (coalesced && side_p) {
 #pragma unroll
-          for (int e8 = 0; e8 < 8; ++e8)
-            sd[e8] = e8 * 4 < ncols ? __ldg(reinterpret_cast<const float4*>(side_p + obase + n0 + e8 * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < 8; ++i)
+            sd[i] = (col_ok && ((rok >> i) & 1u)) ? __ldg(reinterpret_cast<const float4*>(side_p + rbase[i] + n0 + cq * 4))
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         tmem_ld_wait();
         if (p.fuse2) {   // + the hi*lo products (columns [NT, 2*NT)), 16 columns at a time (registers)
@@ -371,27 +413,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           mbar_arrive(&tmem_empty[buf]);
           if (tid == 192) trace_ev(p, 3, ti, 2);
         }
-        if (!SIMPLE && valid && !batched) {
-          // thin / unaligned tiles (C_out = 1, ...): scalar epilogue
-          for (int e = 0; e < ncols; ++e) {
-            const long long o = obase + n0 + e;
-            float v = __uint_as_float(rr[e]);
-            if (p.bias) v += __ldg(p.bias + nt * p.n_stride + n0 + e);
-            if (p.out_act == KT_ACT_LRELU) v = v > 0.f ? v : v * p.out_slope;
-            else if (p.out_act == KT_ACT_TANH) v = tanhf(v);
-            if (p.mask.p) v = side_apply(v, __ldg(p.mask.p + o), p.mask.mode, p.mask.slope);
-            if (p.resid) v += __ldg(p.resid + o);
-            if (p.accumulate) v += p.out[o];
-            p.out[o] = v;
-          }
-        } else if (valid) {
+        if (tid == 192 && ti < 2) trace_ev(p, 4 + ti, n0 >> 5, 1);
+        if (coalesced) {
+          // ---- row-owner layout: bias + output activation, then into the transposition tile
 #pragma unroll
           for (int e8 = 0; e8 < 8; ++e8) {
             const int e = e8 * 4;
-            if (e >= ncols) continue;
-            const long long o = obase + n0 + e;
             float v[4] = {__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3])};
-            if (p.bias) {
+            if (p.bias && e < ncols_t) {
               const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nt * p.n_stride + n0 + e));
               v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
             }
@@ -402,8 +431,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
               for (int z = 0; z < 4; ++z) v[z] = tanhf(v[z]);
             }
+            *reinterpret_cast<float4*>(stg + lane * 32 + ((e8 ^ (lane & 7)) << 2)) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+          __syncwarp();
+          if (tid == 192 && ti < 2) trace_ev(p, 4 + ti, n0 >> 5, 2);
+          // ---- coalesced layout: 8 lanes = one 128-byte row segment
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + (lane >> 3);
+            const float4 t = *reinterpret_cast<const float4*>(stg + row * 32 + ((cq ^ (row & 7)) << 2));
+            float v[4] = {t.x, t.y, t.z, t.w};
             if (side_p) {
-              const float4 a = sd[e8];
+              const float4 a = sd[i];
               if (side_is_mask) {
                 v[0] = side_apply(v[0], a.x, p.mask.mode, p.mask.slope);
                 v[1] = side_apply(v[1], a.y, p.mask.mode, p.mask.slope);
@@ -413,11 +452,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                 v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
               }
             }
-            if (!SIMPLE && p.accumulate) {
-              const float4 a = *reinterpret_cast<const float4*>(p.out + o);
-              v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+            if (col_ok && ((rok >> i) & 1u)) {
+              float* o = p.out + rbase[i] + n0 + cq * 4;
+              if (!SIMPLE && p.accumulate) {
+                const float4 a = *reinterpret_cast<const float4*>(o);
+                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+              }
+              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
             }
-            *reinterpret_cast<float4*>(p.out + o) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+          __syncwarp();      // the tile is rewritten by the next chunk
+          if (tid == 192 && ti < 2) trace_ev(p, 4 + ti, n0 >> 5, 3);
+        } else if (!SIMPLE && valid) {
+          // thin / unaligned tiles (C_out = 1, ...): scalar epilogue
+          const int ncols = max(ncols_t, 0);
+          for (int e = 0; e < ncols; ++e) {
+            const long long o = obase + n0 + e;
+            float v = __uint_as_float(rr[e]);
+            if (p.bias) v += __ldg(p.bias + nt * p.n_stride + n0 + e);
+            if (p.out_act == KT_ACT_LRELU) v = v > 0.f ? v : v * p.out_slope;
+            else if (p.out_act == KT_ACT_TANH) v = tanhf(v);
+            if (p.mask.p) v = side_apply(v, __ldg(p.mask.p + o), p.mask.mode, p.mask.slope);
+            if (p.resid) v += __ldg(p.resid + o);
+            if (p.accumulate) v += p.out[o];
+            p.out[o] = v;
           }
         }
       }
@@ -607,7 +665,7 @@ static int run_tc(TcParams p, cudaStream_t st) {   // p: phases already planned 
   const int a_stage = 2 * p.rows * 128;
   const int b_stage = 2 * p.NT * 128;
   const int slots = p.ntaps * p.kchunks;                                      // weight tiles of the whole layer
-  const int bar_bytes = (2 * 3 + 2 * std::max(6, slots) + 4) * 8 + 16;
+  const int bar_bytes = (2 * 3 + 2 * std::max(6, slots) + 4) * 8 + 16 + kMaxTaps * 4 + 4 * 4096;   // barriers, TMEM slot, tap-shift table, epilogue transposition tiles
   const int budget = kMaxDynSmem - 1024 /*align slack*/ - bar_bytes;
   p.w_resident = 0;
   if (p.ntiles == 1 && slots <= 160 && 2 * a_stage + slots * b_stage <= budget) {

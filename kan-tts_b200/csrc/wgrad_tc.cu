@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   uint64_t* empty = bars + 2;   // [2] MMA -> producers
   uint64_t* tmem_full = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint32_t* s_unit = tmem_slot + 2;     // [kWgMaxUnits] per unit of this CTA: A-side row shift (16-byte units) | LBO field
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cb_tile = blockIdx.x % p.n_cb_tiles;
@@ -90,6 +91,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     fence_proxy_async();
   }
   if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (tid >= 160 && tid < 160 + nu) {
+    const int u = tid - 160;
+    const int n_a = p.unit_tap0[u0 + u];
+    uint32_t lbo_a;
+    if (p.mode == 0) lbo_a = 2u * (uint32_t)img_a;
+    // mode 1: second half of M = the next tap of the same residue (rows 64..127 are discarded when the unit has one tap)
+    else lbo_a = p.unit_ntaps[u0 + u] == 2 ? (uint32_t)((p.tap_q[n_a + 1] - p.tap_q[n_a]) * p.nsub) * 128u : 128u;
+    const uint32_t shift = (uint32_t)((p.tap_q[n_a] - qlo) * p.nsub) * 128u;
+    s_unit[u] = (shift >> 4) + ((lbo_a >> 4) << 16);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -182,41 +193,32 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     tc_fence_before();
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
+    // (descriptor low words + 32-bit adds only, see conv_tc.cu; tap shifts / LBO fields of the units come from a
+    //  shared-memory table filled at kernel start)
     if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(128, p.NT, 1, 1);
-      const uint32_t lbo_b = 2u * (uint32_t)img_b;
+      const uint32_t lbo_b16 = ((2u * (uint32_t)img_b) >> 4) << 16;
+      const uint32_t img_a16 = (uint32_t)img_a >> 4, img_b16 = (uint32_t)img_b >> 4;
+      const uint32_t st16[2] = {smem_u32(stage0) >> 4, smem_u32(stage0 + stage_bytes) >> 4};
+      const uint32_t boff16 = (uint32_t)(p.a_groups * 2 * img_a) >> 4;
       int it = 0;
       for (long long c = c_begin; c < c_end; ++c, ++it) {
         const int s = it & 1;
         mbar_wait(&full[s], (it >> 1) & 1);
         tc_fence_after();
-        const uint32_t st = smem_u32(stage0 + (size_t)s * stage_bytes);
-        const uint32_t b_hi = st + (uint32_t)(p.a_groups * 2 * img_a);
-        const uint32_t b_lo = b_hi + (uint32_t)img_b;
+        const uint32_t b_hi = (st16[s] + boff16) | lbo_b16;
+        uint32_t ua = s_unit[0];
         for (int u = 0; u < nu; ++u) {
-          const int n_a = p.unit_tap0[u0 + u];
-          uint32_t lbo_a;
-          if (p.mode == 0) {
-            lbo_a = 2u * (uint32_t)img_a;
-          } else {
-            // second half of M = the next tap of the same residue (rows 64..127 are discarded when the unit has one tap)
-            lbo_a = p.unit_ntaps[u0 + u] == 2 ? (uint32_t)((p.tap_q[n_a + 1] - p.tap_q[n_a]) * p.nsub) * 128u : 128u;
-          }
-          const uint32_t shift = (uint32_t)((p.tap_q[n_a] - qlo) * p.nsub) * 128u;
-          const uint32_t a_hi = st + shift;
-          const uint32_t a_lo = a_hi + (uint32_t)img_a;
+          const uint32_t a_hi = st16[s] + ua;                 // ua = row shift (16-byte units) | LBO field
+          if (u + 1 < nu) ua = s_unit[u + 1];
           const uint32_t d = tmem_acc + (uint32_t)(u * p.NT);
 #pragma unroll
           for (int ks = 0; ks < kWgTK / 16; ++ks) {
-            const uint32_t ko = (uint32_t)ks * 16u * 128u;
-            const uint64_t da_hi = smem_desc_sw128(a_hi + ko, lbo_a, 1024, false);
-            const uint64_t da_lo = smem_desc_sw128(a_lo + ko, lbo_a, 1024, false);
-            const uint64_t db_hi = smem_desc_sw128(b_hi + ko, lbo_b, 1024, false);
-            const uint64_t db_lo = smem_desc_sw128(b_lo + ko, lbo_b, 1024, false);
+            const uint32_t ko = (uint32_t)ks * 128u;            // 16 rows x 128 bytes, in 16-byte units
             const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
-            umma_bf16(d, da_lo, db_hi, idesc, acc);
-            umma_bf16(d, da_hi, db_lo, idesc, 1);
-            umma_bf16(d, da_hi, db_hi, idesc, 1);
+            umma_bf16_lo(d, a_hi + img_a16 + ko, b_hi + ko, idesc, acc);
+            umma_bf16_lo(d, a_hi + ko, b_hi + img_b16 + ko, idesc, 1u);
+            umma_bf16_lo(d, a_hi + ko, b_hi + ko, idesc, 1u);
           }
         }
         umma_commit(&empty[s]);

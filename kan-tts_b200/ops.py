@@ -190,7 +190,7 @@ class PreparedWeight:
                 nbytes = int(lib.kt_conv1d_tc_image_bytes(ctypes.byref(d), direction))
                 img = torch.empty(nbytes // 2, device=src.device, dtype=torch.bfloat16)
                 self.img[k] = img
-            check(lib.kt_weight_pack_tc(ctypes.byref(d), direction, ptr(src), ptr(img), stream_ptr()),
+            check(lib.kt_weight_pack_tc(ctypes.byref(d), direction, ptr(src), ptr(img, True), stream_ptr()),
                   "kt_weight_pack_tc")
             _count()
             self.img_stale.discard(k)
@@ -214,9 +214,11 @@ def prefetch_weight(cache, spec, v, g):
 def prepare_weight(cache, spec, v, g):
     """v: reference-layout weight (weight_v for weight-norm, the effective weight otherwise);
     g: weight_g or None.  Re-runs the prepare kernel only when a parameter changed."""
-    # only leaf parameters have a trustworthy (data_ptr, version) identity; a recomputed
-    # spectral-norm weight is a fresh tensor every forward and is never cached
-    cacheable = v.is_leaf and (g is None or g.is_leaf)
+    # only nn.Parameters have a trustworthy (data_ptr, version) identity.  A recomputed spectral-norm weight
+    # (`weight_orig / sigma`) is a fresh temporary every forward -- and it IS a leaf whenever weight_orig is frozen or the
+    # call runs under no_grad, so `is_leaf` must not decide this: such a weight is never cached and always gets fresh
+    # buffers (a pending backward of the other half of a (generated, real) pair still holds the previous ones).
+    cacheable = isinstance(v, torch.nn.Parameter) and (g is None or isinstance(g, torch.nn.Parameter))
     key = (v.data_ptr(), v._version, None if g is None else (g.data_ptr(), g._version)) if cacheable else None
     if key is not None and cache.key == key and cache.w_fwd is not None and cache.w_fwd.device == v.device:
         return cache
@@ -285,16 +287,28 @@ _WG_POOL = {}
 _wg_next = 0
 
 
-def _wgrad_stream(device):
-    """Round-robin over a small per-device pool of streams for the weight-gradient chains (wgrad, split-K reduce,
-    bias column sums, weight-norm backward + accumulation): they are leaves of the backward graph, so only the
-    data gradients stay on the critical path and the weight gradients fill otherwise idle SMs."""
-    global _wg_next
+def wgrad_pool(device):
+    """The per-device pool of weight-gradient side streams (created on first use)."""
     pool = _WG_POOL.setdefault((device.type, device.index), [])
     if not pool:
         pool.extend(torch.cuda.Stream(device=device) for _ in range(4))
-    _wg_next = (_wg_next + 1) % len(pool)
-    return pool[_wg_next]
+    return pool
+
+
+def _wgrad_stream(device, param):
+    """A small per-device pool of streams for the weight-gradient chains (wgrad, split-K reduce, bias column sums,
+    weight-norm backward + accumulation): they are leaves of the backward graph, so only the data gradients stay on
+    the critical path and the weight gradients fill otherwise idle SMs.  Every parameter is PINNED to one stream of
+    the pool (assigned round-robin at its first use): the accumulation into ``param.grad`` is a plain read-modify-write,
+    so two chains of the same parameter in one backward (a discriminator applied to y and to y_ in the same graph)
+    must be ordered -- the same stream orders them."""
+    global _wg_next
+    pool = wgrad_pool(device)
+    idx = getattr(param, "_kt_wg_stream", None)
+    if idx is None:
+        _wg_next = (_wg_next + 1) % len(pool)
+        idx = param._kt_wg_stream = _wg_next
+    return pool[idx % len(pool)]
 
 
 def join_wgrad_streams(device=None):
@@ -376,7 +390,7 @@ class ConvFn(torch.autograd.Function):
             global _tc_launches
             img = pw.tc_image(spec, d, 0, nt)
             with _timed("conv_fwd_tc", spec, d):
-                check(lib.kt_conv1d_fwd_tc(ctypes.byref(d), ptr(x), ptr(img), ptr(bd), ptr(resid),
+                check(lib.kt_conv1d_fwd_tc(ctypes.byref(d), ptr(x), ptr(img, True), ptr(bd), ptr(resid),
                                            ptr(y), stream_ptr()), "kt_conv1d_fwd_tc")
             _tc_launches += spec.stride if spec.transposed else 1
         else:
@@ -430,7 +444,7 @@ class ConvFn(torch.autograd.Function):
                 d2 = ctx.d_up
                 dxu = torch.empty((ctx.nb, d2.t_in * d2.nsub, spec.c_in), device=x.device, dtype=torch.float32)
                 with _timed("conv_dgrad_tc", spec, d):
-                    check(lib.kt_conv1d_bwd_data_tc(ctypes.byref(d2), ptr(dy), ptr(y_), ptr(ctx.img_bwd), None,
+                    check(lib.kt_conv1d_bwd_data_tc(ctypes.byref(d2), ptr(dy), ptr(y_), ptr(ctx.img_bwd, True), None,
                                                     ptr(dxu), st), "kt_conv1d_bwd_data_tc")
                     check(lib.kt_upsample_grad_reduce(ptr(dxu), ptr(x_), spec.act_in, spec.act_in_slope, ptr(dx),
                                                       ctx.nb * d.t_in * d.nsub, spec.upsample, spec.c_in, st),
@@ -439,7 +453,7 @@ class ConvFn(torch.autograd.Function):
                 _count()
             elif ctx.nt_bwd:
                 with _timed("conv_dgrad_tc", spec, d):
-                    check(lib.kt_conv1d_bwd_data_tc(ctypes.byref(d), ptr(dy), ptr(y_), ptr(ctx.img_bwd), ptr(x_),
+                    check(lib.kt_conv1d_bwd_data_tc(ctypes.byref(d), ptr(dy), ptr(y_), ptr(ctx.img_bwd, True), ptr(x_),
                                                     ptr(dx), st), "kt_conv1d_bwd_data_tc")
                 _tc_launches += 1
             else:
@@ -455,7 +469,7 @@ class ConvFn(torch.autograd.Function):
             pv, pg, pb = ctx.params
             direct = (need_w and pv.is_leaf and _is_direct(pv) and _is_direct(pg) and (not need_b or _is_direct(pb))
                       and ctx.needs_input_grad[3] and (not ctx.has_g or ctx.needs_input_grad[4]))
-            side = _wgrad_stream(x.device) if (direct and _WGRAD_ASYNC) else None
+            side = _wgrad_stream(x.device, pv) if (direct and _WGRAD_ASYNC) else None
             if side is not None:
                 # nothing of this chain is handed back to autograd (the kernels accumulate into param.grad), so it
                 # runs on a side stream; join_wgrad_streams() orders it before the optimizer

@@ -100,7 +100,7 @@ class SelfAttnFn(torch.autograd.Function):
         probs = torch.empty(n_head * B, L, L, device=qkv.device, dtype=torch.float32)
         keep = _u8(keep) if keep is not None else _keep_mask(p_drop, probs.shape, qkv.device)
         dropped = torch.empty_like(probs) if keep is not None else None
-        check(lib.kt_attention_fwd(ctypes.byref(d), _off(qkv, 0), _off(qkv, hd), _off(qkv, 2 * hd), ptr(m), ptr(keep),
+        check(lib.kt_attention_fwd(ctypes.byref(d), _off(qkv, 0), _off(qkv, hd), _off(qkv, 2 * hd), ptr(m, True), ptr(keep, True),
                                    ptr(out), ptr(probs), ptr(dropped), stream_ptr()), "kt_attention_fwd")
         _count()
         ctx.d, ctx.hd = d, hd
@@ -118,7 +118,7 @@ class SelfAttnFn(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         delta = torch.empty(d.heads * d.batch * d.lq, device=qkv.device, dtype=torch.float32)
         check(lib.kt_attention_bwd(ctypes.byref(d), _off(qkv, 0), _off(qkv, hd), _off(qkv, 2 * hd), ptr(probs),
-                                   ptr(keep), ptr(dout), _off(dqkv, 0), _off(dqkv, hd), _off(dqkv, 2 * hd),
+                                   ptr(keep, True), ptr(dout), _off(dqkv, 0), _off(dqkv, hd), _off(dqkv, 2 * hd),
                                    ptr(delta), 0, stream_ptr()), "kt_attention_bwd")
         _count(2)
         return dqkv, None, None, None, None
@@ -149,10 +149,10 @@ class PncaAttnFn(torch.autograd.Function):
         pxd = torch.empty_like(px) if kx is not None else None
         phd = torch.empty_like(ph) if kh is not None else None
         st = stream_ptr()
-        check(lib.kt_attention_fwd(ctypes.byref(dx), _off(x_qkv, 0), _off(x_qkv, hd), _off(x_qkv, 2 * hd), ptr(mx),
-                                   ptr(kx), ptr(out_x), ptr(px), ptr(pxd), st), "kt_attention_fwd")
-        check(lib.kt_attention_fwd(ctypes.byref(dh), _off(x_qkv, 0), _off(h_kv, 0), _off(h_kv, hd), ptr(mh),
-                                   ptr(kh), ptr(out_h), ptr(ph), ptr(phd), st), "kt_attention_fwd")
+        check(lib.kt_attention_fwd(ctypes.byref(dx), _off(x_qkv, 0), _off(x_qkv, hd), _off(x_qkv, 2 * hd), ptr(mx, True),
+                                   ptr(kx, True), ptr(out_x), ptr(px), ptr(pxd), st), "kt_attention_fwd")
+        check(lib.kt_attention_fwd(ctypes.byref(dh), _off(x_qkv, 0), _off(h_kv, 0), _off(h_kv, hd), ptr(mh, True),
+                                   ptr(kh, True), ptr(out_h), ptr(ph), ptr(phd), st), "kt_attention_fwd")
         _count(2)
         ctx.dx, ctx.dh, ctx.hd = dx, dh, hd
         ctx.save_for_backward(x_qkv, h_kv, px, ph, kx, kh)
@@ -172,10 +172,10 @@ class PncaAttnFn(torch.autograd.Function):
         delta = torch.empty(dx.heads * dx.batch * dx.lq, device=x_qkv.device, dtype=torch.float32)
         st = stream_ptr()
         check(lib.kt_attention_bwd(ctypes.byref(dx), _off(x_qkv, 0), _off(x_qkv, hd), _off(x_qkv, 2 * hd), ptr(px),
-                                   ptr(kx), ptr(dox), _off(dqkv, 0), _off(dqkv, hd), _off(dqkv, 2 * hd), ptr(delta), 0,
+                                   ptr(kx, True), ptr(dox), _off(dqkv, 0), _off(dqkv, hd), _off(dqkv, 2 * hd), ptr(delta), 0,
                                    st), "kt_attention_bwd")
         check(lib.kt_attention_bwd(ctypes.byref(dh), _off(x_qkv, 0), _off(h_kv, 0), _off(h_kv, hd), ptr(ph),
-                                   ptr(kh), ptr(doh), _off(dqkv, 0), _off(dhkv, 0), _off(dhkv, hd), ptr(delta), 1, st),
+                                   ptr(kh, True), ptr(doh), _off(dqkv, 0), _off(dhkv, 0), _off(dhkv, hd), ptr(delta), 1, st),
               "kt_attention_bwd")
         _count(4)
         return dqkv, dhkv, None, None, None, None, None, None
@@ -202,9 +202,9 @@ def pnca_attn_step(q_row, x_cache, h_kv, mask_x, mask_h, n_head):
     px = torch.empty(n_head * B, 1, lmax, device=q_row.device, dtype=torch.float32)
     ph = torch.empty(n_head * B, 1, lh, device=q_row.device, dtype=torch.float32)
     st = stream_ptr()
-    check(lib.kt_attention_fwd(ctypes.byref(dx), _off(q_row, 0), _off(x_cache, hd), _off(x_cache, 2 * hd), ptr(mx), None,
+    check(lib.kt_attention_fwd(ctypes.byref(dx), _off(q_row, 0), _off(x_cache, hd), _off(x_cache, 2 * hd), ptr(mx, True), None,
                                ptr(out_x), ptr(px), None, st), "kt_attention_fwd")
-    check(lib.kt_attention_fwd(ctypes.byref(dh), _off(q_row, 0), _off(h_kv, 0), _off(h_kv, hd), ptr(mh), None,
+    check(lib.kt_attention_fwd(ctypes.byref(dh), _off(q_row, 0), _off(h_kv, 0), _off(h_kv, hd), ptr(mh, True), None,
                                ptr(out_h), ptr(ph), None, st), "kt_attention_fwd")
     _count(2)
     return out_x, out_h, px, ph
@@ -221,7 +221,7 @@ class FsmnMemoryFn(torch.autograd.Function):
         K = w.shape[-1]
         m = _u8(mask)
         y = torch.empty_like(x)
-        check(lib.kt_fsmn_fwd(ptr(x), ptr(w.detach().contiguous()), ptr(m), ptr(y), B, T, C, K, pad_left,
+        check(lib.kt_fsmn_fwd(ptr(x), ptr(w.detach().contiguous()), ptr(m, True), ptr(y), B, T, C, K, pad_left,
                               stream_ptr()), "kt_fsmn_fwd")
         _count()
         ctx.pad_left = pad_left
@@ -242,7 +242,7 @@ class FsmnMemoryFn(torch.autograd.Function):
             dw = torch.empty_like(w)
             n = int(lib.kt_fsmn_bwd_workspace(B, T, C, K))
             ws = torch.empty(n, device=x.device, dtype=torch.float32)
-        check(lib.kt_fsmn_bwd(ptr(x), ptr(dy), ptr(w.detach().contiguous()), ptr(m), ptr(dx), ptr(dw), ptr(ws), n,
+        check(lib.kt_fsmn_bwd(ptr(x), ptr(dy), ptr(w.detach().contiguous()), ptr(m, True), ptr(dx), ptr(dw), ptr(ws), n,
                               B, T, C, K, ctx.pad_left, stream_ptr()), "kt_fsmn_bwd")
         _count(3)
         return dx, dw, None, None
@@ -259,7 +259,7 @@ class RowsGatherFn(torch.autograd.Function):
         B, T_in, C = x.shape
         T_out = idx.shape[1]
         out = torch.empty(B, T_out, C, device=x.device, dtype=torch.float32)
-        check(lib.kt_rows_gather_fwd(ptr(x), ptr(idx), ptr(out), B, T_out, T_in, C, stream_ptr()),
+        check(lib.kt_rows_gather_fwd(ptr(x), ptr(idx, True), ptr(out), B, T_out, T_in, C, stream_ptr()),
               "kt_rows_gather_fwd")
         _count()
         ctx.save_for_backward(idx, start, count)
@@ -273,7 +273,7 @@ class RowsGatherFn(torch.autograd.Function):
         dout = dout.contiguous()
         B, T_out, C = dout.shape
         din = torch.empty(B, ctx.t_in, C, device=dout.device, dtype=torch.float32)
-        check(lib.kt_rows_gather_bwd(ptr(dout), ptr(idx), ptr(start), ptr(count), ptr(din), B, T_out, ctx.t_in, C,
+        check(lib.kt_rows_gather_bwd(ptr(dout), ptr(idx, True), ptr(start, True), ptr(count, True), ptr(din), B, T_out, ctx.t_in, C,
                                      stream_ptr()), "kt_rows_gather_bwd")
         _count()
         return din, None, None, None

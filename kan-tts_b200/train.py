@@ -184,10 +184,7 @@ class GanStep:
             return None
         from . import hifigan
         cur = torch.cuda.current_stream()
-        key = (t.device.type, t.device.index)
-        if key not in ops._WG_POOL:
-            ops._wgrad_stream(t.device)
-        streams = ops._WG_POOL[key]
+        streams = ops.wgrad_pool(t.device)
         for s in streams:
             s.wait_stream(cur)
         for m in modules:

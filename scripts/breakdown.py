@@ -16,6 +16,10 @@ y, x = y.to(dev), x.to(dev)
 for _ in range(2):
     step.step((y, x))
 torch.cuda.synchronize()
+from kantts_b200 import hifigan
+hifigan._PARALLEL_STREAMS, ops._WGRAD_ASYNC = False, False     # serialise: an event pair must bracket only its own kernels
+step.step((y, x))
+torch.cuda.synchronize()
 prof = ops.set_profiler(True)
 step.step((y, x))
 by = prof.by_layer()

@@ -30,8 +30,8 @@ def run(name, iters):
     spec.act_out, spec.act_out_slope = KT_ACT_LRELU, 0.1
     g = torch.Generator().manual_seed(1)
     wshape = (spec.c_out, spec.c_in // spec.groups, spec.kernel)
-    v = (torch.randn(wshape, generator=g) * 0.05).cuda().requires_grad_(True)
-    gg = v.detach().norm(2, dim=(1, 2), keepdim=True).clone().requires_grad_(True)
+    v = torch.nn.Parameter((torch.randn(wshape, generator=g) * 0.05).cuda())
+    gg = torch.nn.Parameter(v.detach().norm(2, dim=(1, 2), keepdim=True).clone())
     bias = torch.zeros(spec.c_out, device="cuda", requires_grad=True)
     xs = (B, T, period, spec.c_in) if period else (B, T, spec.c_in)
     x = torch.randn(xs, generator=g).cuda().requires_grad_(True)

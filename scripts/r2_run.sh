@@ -1,0 +1,20 @@
+#!/bin/bash
+# round-2 GPU run helper: $1 = run tag; remaining args select legs (tests unverified trace layers bench ncu_list)
+TAG=$1; shift
+mkdir -p gpurun_out; S=gpurun_out/summary_$TAG.txt; rm -f $S
+for leg in "$@"; do
+  case $leg in
+    tests) timeout 900 python -m pytest tests -m gpu -q --tb=short -x > gpurun_out/tests_$TAG.log 2>&1; echo "tests rc=$?" >> $S
+           grep -E "passed|failed|^FAILED|^ERROR" gpurun_out/tests_$TAG.log | cut -c1-300 | head -30 >> $S ;;
+    unverified) KANTTS_B200_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_pipeline.py -m gpu -q --tb=short > gpurun_out/unverified_$TAG.log 2>&1; echo "unverified rc=$?" >> $S
+           grep -E "passed|failed|^FAILED|^ERROR" gpurun_out/unverified_$TAG.log | cut -c1-300 | head -30 >> $S ;;
+    trace) timeout 300 python scripts/tc_trace.py > gpurun_out/tc_trace_$TAG.log 2>&1; echo "trace rc=$?" >> $S ;;
+    layers) timeout 300 python scripts/layer_bench.py > gpurun_out/layers_$TAG.log 2>&1; echo "layers rc=$?" >> $S ;;
+    smoke) timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?" >> $S ;;
+    bench) timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.log 2>&1; echo "bench rc=$?" >> $S ;;
+    breakdown) timeout 600 python scripts/breakdown.py > gpurun_out/breakdown_$TAG.log 2>&1; echo "breakdown rc=$?" >> $S ;;
+    ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --ncu --steps 1 > gpurun_out/ncu_list_$TAG.log 2>&1; echo "ncu list rc=$?" >> $S ;;
+    *) echo "unknown leg $leg" >> $S ;;
+  esac
+done
+cat $S

@@ -24,7 +24,7 @@ for name, (kw, B, T, period, resid) in LAYERS.items():
     else:
         spec.act_out, spec.act_out_slope = KT_ACT_LRELU, 0.1
     g = torch.Generator().manual_seed(1)
-    v = (torch.randn((spec.c_out, spec.c_in // spec.groups, spec.kernel), generator=g) * 0.05).cuda()
+    v = torch.nn.Parameter((torch.randn((spec.c_out, spec.c_in // spec.groups, spec.kernel), generator=g) * 0.05).cuda(), requires_grad=False)
     bias = torch.zeros(spec.c_out, device="cuda")
     xs = (B, T, period, spec.c_in) if period else (B, T, spec.c_in)
     x = torch.randn(xs, generator=g).cuda()
@@ -41,12 +41,12 @@ for name, (kw, B, T, period, resid) in LAYERS.items():
             y = ops.conv(x, spec, cache, v, None, bias, r)
         e1.record(); torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 100
-        tr = torch.zeros(5 * 16 * 4, dtype=torch.int64, device="cuda")
+        tr = torch.zeros(6 * 16 * 4, dtype=torch.int64, device="cuda")
         lib.kt_debug_set_trace(tr.data_ptr())
         y = ops.conv(x, spec, cache, v, None, bias, r)
         torch.cuda.synchronize()
         lib.kt_debug_set_trace(None)
-    t = tr.cpu().view(5, 16, 4)
+    t = tr.cpu().view(6, 16, 4)
     t0 = int(t[t > 0].min())
     rel = lambda a: "   -  " if a == 0 else f"{(a - t0) / 1.9e3:6.1f}"
     print(f"=== {name}: {us:.1f} us/launch (warm, back to back); CTA0 timeline in us (clock64 / 1.9 GHz)")
@@ -57,8 +57,9 @@ for name, (kw, B, T, period, resid) in LAYERS.items():
         for role, nm in ((0, "P0"), (1, "P1"), (2, "MMA"), (3, "EPI")):
             row.append(nm + ":" + " ".join(rel(int(t[role, ti, e])) for e in range(4 if role >= 2 else 2)))
         print(f"  tile {ti}: " + " | ".join(row))
-    taps = [n for n in range(16) if int(t[4, n].max()) > 0]
-    if taps:
-        print("  MMA issuer, tile 1, chunk 0, per tap (us): before weight wait / after wait / MMAs issued / after commit")
-        for n in taps:
-            print(f"    tap {n:2d}: " + " ".join(rel(int(t[4, n, e])) for e in range(4)))
+    for role, ttl in ((4, "tile 0"), (5, "tile 1")):
+        chunks = [n for n in range(16) if int(t[role, n].max()) > 0]
+        if chunks:
+            print(f"  epilogue warp 0, {ttl}, per 32-column chunk (us): start / TMEM loaded (+fuse2 add) / transposed / stored")
+            for n in chunks:
+                print(f"    chunk {n:2d}: " + " ".join(rel(int(t[role, n, e])) for e in range(4)))

@@ -294,12 +294,18 @@ def test_forward_pair_equals_two_calls(golden, name, cls):
     ya = (0.3 * torch.randn(3, 1, T)).to(DEV).requires_grad_(True)
     yb = (0.3 * torch.randn(3, 1, T)).to(DEV)
     res = {}
-    for mode in ("two", "pair"):
+    for mode in ("two", "pair", "two_frozen", "pair_frozen"):
         d = getattr(K, cls)(**g.cfg).to(DEV)
         d.load_state_dict(g.group("sd/"))
         d.train()
+        if mode.endswith("frozen"):
+            # GanStep's generator phase freezes D (skip_unused_d_grads): the recomputed spectral-norm weight is then a
+            # LEAF temporary; it must still get fresh prepared buffers per forward (the first half's backward is pending
+            # while the second half's forward re-runs the power iteration) -- ADVICE r1, ops.prepare_weight
+            for q in d.parameters():
+                q.requires_grad_(False)
         ya.grad = None
-        if mode == "two":
+        if mode.startswith("two"):
             oa, fa = d(ya)
             with torch.no_grad():
                 ob, fb = d(yb)
@@ -311,12 +317,13 @@ def test_forward_pair_equals_two_calls(golden, name, cls):
         res[mode] = ([o.detach().clone() for o in oa], [o.detach().clone() for o in ob],
                      [f.detach().clone() for fm in fa for f in fm], [f.detach().clone() for fm in fb for f in fm],
                      ya.grad.clone(), {k: v.clone() for k, v in d.state_dict().items() if k.endswith(("weight_u", "weight_v"))})
-    for i in range(4):
-        for a, b in zip(res["two"][i], res["pair"][i]):
-            assert a.shape == b.shape and rel_l2(b, a) < 1e-4, (i, rel_l2(b, a))
-    assert rel_l2(res["pair"][4], res["two"][4]) < 1e-4
-    for k, v in res["two"][5].items():
-        assert rel_l2(res["pair"][5][k], v) < 1e-5, k
+    for mode in ("pair", "two_frozen", "pair_frozen"):
+        for i in range(4):
+            for a, b in zip(res["two"][i], res[mode][i]):
+                assert a.shape == b.shape and rel_l2(b, a) < 1e-4, (mode, i, rel_l2(b, a))
+        assert rel_l2(res[mode][4], res["two"][4]) < 1e-4, (mode, rel_l2(res[mode][4], res["two"][4]))
+        for k, v in res["two"][5].items():
+            assert rel_l2(res[mode][5][k], v) < 1e-5, (mode, k)
 
 
 def test_direct_grad_accumulation_matches_autograd(golden):

@@ -1,19 +1,13 @@
 """BASELINE configs[4] shape of flow: symbols -> SAM-BERT free-running decode -> mel -> HiFi-GAN generator -> wav, for a
 ragged batch, against the CPU oracle's composition of the same two restatements.
 
-Written after the round's GPU budget was spent: its parts are covered by the green tests (SAM-BERT batch inference vs the
-oracle, generator forward vs the reference goldens); the glue (transpose + per-utterance cut) has not run on a GPU yet,
-so the test is opt-in until it has: KANTTS_B200_TEST_UNVERIFIED=1."""
-import os
-
+(First green GPU run: round 2, gpurun call r2a -- 3 passed.)"""
 import pytest
 import torch
 
 from conftest import rel_l2
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("KANTTS_B200_TEST_UNVERIFIED") != "1",
-                                 reason="not yet run on a GPU: set KANTTS_B200_TEST_UNVERIFIED=1")]
+pytestmark = [pytest.mark.gpu]
 
 
 def test_synthesize_matches_oracle_composition(golden):

@@ -119,6 +119,33 @@ def test_dwt_properties():
     assert abs(float((yl.pow(2).sum() + yh.pow(2).sum()) / x.pow(2).sum()) - 1) < 1e-10
 
 
+def test_dwt_against_independent_derivation():
+    """Pin of row D3 that does not go through oracle/dwt.py's own arithmetic (the reference-shim goldens are
+    circular for the DWT).  (1) The db3 taps from Daubechies' closed form for N = 3 (spectral factorisation of
+    1 + 3y + 6y^2: Daubechies, "Ten Lectures on Wavelets", table 6.1) must reproduce the PyWavelets table used by the
+    oracle and the CUDA kernel.  (2) PyWavelets' documented definition of the zero-mode analysis step -- the FULL linear
+    convolution with the decomposition filter, keeping the odd samples, floor((N + 5) / 2) coefficients -- evaluated
+    with numpy.convolve must equal the oracle's strided-conv1d-on-a-padded-signal formulation, for even and odd N."""
+    s10 = 10 ** 0.5
+    r = (5 + 2 * s10) ** 0.5
+    rec_lo = np.array([1 + s10 + r, 5 + s10 + 3 * r, 10 - 2 * s10 + 2 * r, 10 - 2 * s10 - 2 * r, 5 + s10 - 3 * r,
+                       1 + s10 - r]) / (16 * 2 ** 0.5)
+    dec_lo = rec_lo[::-1]
+    dec_hi = np.array([(-1) ** (k + 1) * rec_lo[k] for k in range(6)])     # quadrature mirror of the scaling filter
+    # (PyWavelets tabulates the taps to ~1e-11; far below fp32 resolution)
+    assert np.abs(dec_lo - np.array(ODWT.DEC_LO)).max() < 1e-10
+    assert np.abs(dec_hi - np.array(ODWT.DEC_HI)).max() < 1e-10
+    rng = np.random.default_rng(3)
+    for n in (8192, 4098, 2051, 17, 6, 5):
+        x = rng.standard_normal(n)
+        want_lo = np.convolve(x, dec_lo)[1::2]
+        want_hi = np.convolve(x, dec_hi)[1::2]
+        yl, yh = ODWT.dwt_db3_zero(torch.from_numpy(x).view(1, 1, n))
+        assert want_lo.shape[0] == (n + 5) // 2 == yl.shape[-1]
+        assert np.abs(yl.numpy().ravel() - want_lo).max() < 1e-9, n
+        assert np.abs(yh.numpy().ravel() - want_hi).max() < 1e-9, n
+
+
 def test_mel_basis_matches_torchaudio():
     ta = pytest.importorskip("torchaudio")
     for sr, n_fft, n_mels, fmin, fmax in [(22050, 1024, 80, 80, 7600), (24000, 1024, 80, 0, 8000), (16000, 2048, 80, 0, 8000)]:
