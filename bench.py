@@ -143,6 +143,44 @@ def reference_main(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def torch_gpu_main(args, rank, local_rank):
+    """the same workload on stock PyTorch library kernels (cuDNN / cuBLAS / cuFFT, fp32, TF32 off,
+    cudnn.benchmark) on ONE B200 -- "the practical kernel to beat".  Informational: printed with impl = torch_gpu and the
+    key gpu_library_baseline; never part of the product path."""
+    if rank != 0:
+        return
+    from baseline.torch_gan import TorchGanStep
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(1234)
+    st = TorchGanStep(dev)
+    y, x = synth_batch(B_PER_GPU, 1234)
+    y, x = y.to(dev), x.to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev, dtype=torch.float32)
+    W = max(3, args.warmup)
+    for _ in range(W):
+        st.step((y, x))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        flush.zero_()
+        gl, dl = st.step((y, x))
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    val = B_PER_GPU * T_WAV / (ms * 1e-3)
+    print(json.dumps({"impl": "torch_gpu", "metric": "hifigan_train_step_audio_samples_per_sec", "value": val,
+                      "unit": "samples/s", "n_gpus": 1, "steps": args.steps, "warmup": W, "ms_per_step": ms,
+                      "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU, "segment": T_WAV,
+                                 "note": "stock torch.nn modules (baseline/torch_gan.py), cuDNN fp32, TF32 disabled, "
+                                         "cudnn.benchmark on, eager; 256 MB L2 flush between steps"},
+                      "gpu_library_baseline": {"value": val, "unit": "samples/s", "ms_per_step": ms,
+                                               "torch": torch.__version__, "cudnn": torch.backends.cudnn.version()},
+                      "losses": {"generator": float(gl), "discriminator": float(dl)}}), flush=True)
+
+
 # ---------------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------------
@@ -190,7 +228,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "torch_gpu"],
+                    help="native: this repo's CUDA path; reference: the reference's CPU path (oracle port) on the host cores; "
+                         "torch_gpu: stock PyTorch (cuDNN fp32, TF32 off) on the same GPU -- informational baseline")
     ap.add_argument("--cpu-sample-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -207,6 +247,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", rank))
     if args.impl == "reference":
         return reference_main(args, rank)
+    if args.impl == "torch_gpu":
+        return torch_gpu_main(args, rank, local_rank)
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torchrun (one rank per GPU)")
     if not torch.cuda.is_available():

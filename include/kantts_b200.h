@@ -259,10 +259,38 @@ int kt_rows_gather_fwd(const float* in, const int32_t* idx, float* out, int32_t 
 int kt_rows_gather_bwd(const float* dout, const int32_t* idx, const int32_t* start, const int32_t* count, float* din,
                        int32_t batch, int32_t t_out, int32_t t_in, int32_t c, void* stream);
 
+/* ---- fused ResidualBlock unit (kantts/models/hifigan/layers.py:213-220, one (convs1[i], convs2[i]) pair) ----------
+ *   h = conv(leaky_relu(x); w1, dilation d, pad_left1) + b1
+ *   y = conv(leaky_relu(h); w2, dilation 1, pad_left2) + b2 + x
+ * x, h, y: [B][T][C] channels-last fp32; C = 32 or 64, odd kernel <= 15; pad_left = (k-1)*dil for the causal variant
+ * (layers.py:66), (k-1)*dil/2 otherwise; out-of-range taps read 0.  ONE launch on the tcgen05 path (bf16x3): the
+ * intermediate stays in shared memory / TMEM.  kt_resblock_pack turns a conv's fp32 kernel-layout weight
+ * ([k][C][C], kt_weight_prepare's w_fwd) into the kernel's weight image (kt_resblock_image_bytes bytes).
+ * `h` (optional, may be NULL) receives the first conv's output for the backward pass. */
+typedef struct KtResblockDesc {
+  int32_t batch, t, channels, kernel, dilation, pad_left1, pad_left2;
+  float slope;   /* LeakyReLU negative slope of both pre-activations */
+  int32_t path;  /* KT_PATH_* (FFMA: the fused kernel is not available) */
+} KtResblockDesc;
+int kt_resblock_plan(const KtResblockDesc* d);                 /* 1: the fused kernel supports this shape */
+int64_t kt_resblock_image_bytes(const KtResblockDesc* d);      /* per conv; 0 = unsupported */
+int kt_resblock_pack(const KtResblockDesc* d, const float* w_fwd, void* img, void* stream);
+int kt_resblock_fwd(const KtResblockDesc* d, const float* x, const void* img1, const float* b1, const void* img2,
+                    const float* b2, float* h, float* y, void* stream);
+/* Backward of the unit from the saved (x, h): the data gradients of both convs (tcgen05 kernels, derivative masks and
+ * the residual path fused) -- dh = c2^T(dy) * lrelu'(h) is written to `dh` (the weight-gradient kernels of c1 need it),
+ * dx = dy + c1^T(dh) * lrelu'(x).  wimg*_bwd: kt_weight_pack_tc(dir = 1) images of the two convs' descriptors d1 / d2
+ * (the per-conv descriptors the weight-gradient entry points also take). */
+int kt_resblock_bwd(const KtConv1dDesc* d1, const KtConv1dDesc* d2, const float* x, const float* h, const float* dy,
+                    const void* wimg1_bwd, const void* wimg2_bwd, float* dh, float* dx, void* stream);
+
 /* Development aid: when dev_buf is non-NULL, CTA 0 of every following kt_conv1d_{fwd,bwd_data}_tc launch records
  * clock64() timestamps per role / tile / event into it (int64 [4 roles][16 tiles][4 events]; scripts/tc_trace.py).
  * Process-global and not thread-safe; pass NULL to switch it off (the default). */
 int kt_debug_set_trace(void* dev_buf);
+/* Development aid: ablation switches of the tcgen05 conv kernel's epilogue for timing experiments (bit 0: no residual /
+ * mask loads, 1: no global stores, 2: no transposition, 3: no TMEM loads).  RESULTS ARE WRONG while non-zero. */
+int kt_debug_set_flags(int32_t flags);
 
 /* library info */
 const char* kt_last_error(void);

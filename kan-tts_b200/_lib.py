@@ -15,7 +15,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkantts_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
-SOURCES = ["api.cu", "conv_ffma.cu", "conv_tc.cu", "wgrad_tc.cu", "weights.cu", "misc.cu", "stft_mel.cu", "sambert.cu", "thin.cu"]
+SOURCES = ["api.cu", "conv_ffma.cu", "conv_tc.cu", "resblock_tc.cu", "wgrad_tc.cu", "weights.cu", "misc.cu", "stft_mel.cu", "sambert.cu", "thin.cu"]
 
 KT_ACT_NONE, KT_ACT_LRELU, KT_ACT_TANH = 0, 1, 2
 KT_PATH_AUTO, KT_PATH_FFMA, KT_PATH_TC = 0, 1, 2
@@ -27,6 +27,11 @@ class KtConv1dDesc(ctypes.Structure):
                  "dilation", "pad_left", "transposed", "upsample", "act_in")] + \
                [("act_in_slope", ctypes.c_float), ("act_out", ctypes.c_int32),
                 ("act_out_slope", ctypes.c_float), ("path", ctypes.c_int32)]
+
+
+class KtResblockDesc(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("batch", "t", "channels", "kernel", "dilation", "pad_left1", "pad_left2")] + \
+               [("slope", ctypes.c_float), ("path", ctypes.c_int32)]
 
 
 class KtMelDesc(ctypes.Structure):
@@ -69,6 +74,11 @@ PROTOTYPES = {
     "kt_conv1d_bwd_data_tc": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P],
     "kt_conv1d_bwd_weight_tc_workspace": [ctypes.POINTER(KtConv1dDesc)],
     "kt_conv1d_bwd_weight_tc": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P, _L, _P],
+    "kt_resblock_plan": [ctypes.POINTER(KtResblockDesc)],
+    "kt_resblock_image_bytes": [ctypes.POINTER(KtResblockDesc)],
+    "kt_resblock_pack": [ctypes.POINTER(KtResblockDesc), _P, _P, _P],
+    "kt_resblock_fwd": [ctypes.POINTER(KtResblockDesc), _P, _P, _P, _P, _P, _P, _P, _P],
+    "kt_resblock_bwd": [ctypes.POINTER(KtConv1dDesc), ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P, _P, _P],
     "kt_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _I, _I, _F, _P],
     "kt_layernorm_bwd_workspace": [_I, _I],
     "kt_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _P],
@@ -80,6 +90,7 @@ PROTOTYPES = {
     "kt_rows_gather_fwd": [_P, _P, _P, _I, _I, _I, _I, _P],
     "kt_rows_gather_bwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "kt_debug_set_trace": [_P],
+    "kt_debug_set_flags": [_I],
     "kt_version": [],
     "kt_has_tc": [],
 }

@@ -23,10 +23,15 @@ long long wgrad_tc_workspace(const KtConv1dDesc*);
 int conv1d_bwd_weight_tc(const KtConv1dDesc*, const float*, const float*, const float*, float*, float*, float*, long long, cudaStream_t);
 int tc_plan(const KtConv1dDesc*, int);
 void debug_set_trace(long long*);
+void debug_set_flags(int);
 long long tc_image_bytes(const KtConv1dDesc*, int);
 int tc_pack_layer(const KtConv1dDesc*, int, const float*, void*, cudaStream_t);
 int conv1d_fwd_tc(const KtConv1dDesc*, const float*, const void*, const float*, const float*, float*, cudaStream_t);
 int conv1d_bwd_data_tc(const KtConv1dDesc*, const float*, const float*, const void*, const float*, float*, cudaStream_t);
+int resblock_plan(const KtResblockDesc*);
+long long resblock_image_bytes(const KtResblockDesc*);
+int resblock_pack(const KtResblockDesc*, const float*, void*, cudaStream_t);
+int resblock_fwd(const KtResblockDesc*, const float*, const void*, const float*, const void*, const float*, float*, float*, cudaStream_t);
 int layernorm_fwd(const float*, const float*, const float*, float*, float*, float*, int, int, float, cudaStream_t);
 long long layernorm_bwd_workspace(int, int);
 int layernorm_bwd(const float*, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
@@ -102,6 +107,10 @@ int kt_debug_set_trace(void* dev_buf) {
   kt::debug_set_trace(reinterpret_cast<long long*>(dev_buf));
   return KT_OK;
 }
+int kt_debug_set_flags(int32_t flags) {
+  kt::debug_set_flags(flags);
+  return KT_OK;
+}
 int kt_upsample_grad_reduce(const float* dxu, const float* x, int32_t act_in, float act_in_slope, float* dx, int64_t rows,
                             int32_t up, int32_t c, void* stream) {
   return kt::upsample_grad_reduce(dxu, x, act_in, act_in_slope, dx, rows, up, c, ST(stream));
@@ -161,6 +170,33 @@ int kt_conv1d_bwd_data_tc(const KtConv1dDesc* d, const float* dy, const float* y
   if (rc) return rc;
   KT_REQUIRE(dy && wimg && dx, "kt_conv1d_bwd_data_tc: null pointer");
   return kt::conv1d_bwd_data_tc(d, dy, y, wimg, x, dx, ST(stream));
+}
+
+int kt_resblock_plan(const KtResblockDesc* d) { return d ? kt::resblock_plan(d) : 0; }
+int64_t kt_resblock_image_bytes(const KtResblockDesc* d) { return d ? kt::resblock_image_bytes(d) : 0; }
+int kt_resblock_pack(const KtResblockDesc* d, const float* w_fwd, void* img, void* stream) {
+  KT_REQUIRE(d, "kt_resblock_pack: null descriptor");
+  return kt::resblock_pack(d, w_fwd, img, ST(stream));
+}
+int kt_resblock_fwd(const KtResblockDesc* d, const float* x, const void* img1, const float* b1, const void* img2,
+                    const float* b2, float* h, float* y, void* stream) {
+  KT_REQUIRE(d, "kt_resblock_fwd: null descriptor");
+  return kt::resblock_fwd(d, x, img1, b1, img2, b2, h, y, ST(stream));
+}
+int kt_resblock_bwd(const KtConv1dDesc* d1, const KtConv1dDesc* d2, const float* x, const float* h, const float* dy,
+                    const void* wimg1_bwd, const void* wimg2_bwd, float* dh, float* dx, void* stream) {
+  KT_REQUIRE(d1 && d2 && x && h && dy && wimg1_bwd && wimg2_bwd && dh && dx, "kt_resblock_bwd: null pointer");
+  KT_REQUIRE(d1->act_in == KT_ACT_LRELU && d2->act_in == KT_ACT_LRELU && d1->act_out == KT_ACT_NONE && d2->act_out == KT_ACT_NONE &&
+                 d1->c_in == d1->c_out && d2->c_in == d2->c_out && d1->c_in == d2->c_in && d1->t_in == d2->t_in && d1->t_out == d1->t_in &&
+                 d2->t_out == d2->t_in && d1->batch == d2->batch && d1->nsub == 1 && d2->nsub == 1,
+             "kt_resblock_bwd: descriptors are not a (convs1[i], convs2[i]) pair of a ResidualBlock");
+  // dh = c2^T(dy) * lrelu'(h);  dx = c1^T(dh) * lrelu'(x) + dy   (the residual path, layers.py:219)
+  int rc = kt::conv1d_bwd_data_tc(d2, dy, nullptr, wimg2_bwd, h, dh, ST(stream));
+  if (rc) return rc;
+  rc = kt::conv1d_bwd_data_tc(d1, dh, nullptr, wimg1_bwd, x, dx, ST(stream));
+  if (rc) return rc;
+  const long long n = (long long)d1->batch * d1->t_in * d1->c_in;
+  return kt::add3_scale(dx, dy, nullptr, 1.f, dx, n, ST(stream));
 }
 
 int kt_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean, float* rstd,

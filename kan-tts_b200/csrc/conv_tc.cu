@@ -125,6 +125,7 @@ struct TcParams {
   int tap_shift[kMaxTaps];            // image row shift (q_n - q_lo) * nsub
   // development aid (kt_debug_set_trace): CTA 0 records clock64() per role / tile / event, see scripts/tc_trace.py
   long long* trace;
+  int dbg;      // development aid (kt_debug_set_flags): ablation switches for timing experiments, results are WRONG when non-zero
 };
 
 constexpr int kTraceTiles = 16, kTraceEvents = 4;
@@ -134,8 +135,9 @@ __device__ __forceinline__ void trace_ev(const TcParams& p, int role, int tile_i
 }
 
 // warps 0-3 and 10-13 stage activations (two producer groups filling ALTERNATE pipeline stages, so two images'
-// worth of global loads are in flight), 4 streams weights, 5 issues MMAs, 6-9 epilogue
-constexpr int kTcThreads = 448;
+// worth of global loads are in flight), 4 streams weights, 5 issues MMAs, 6-9 and 14-17 epilogue (two groups
+// draining ALTERNATE tiles = TMEM accumulator buffers)
+constexpr int kTcThreads = 576;
 
 // Persistent: gridDim.x = min(#tiles, #SMs); each CTA walks tiles blockIdx.x, +gridDim.x, ...  The three
 // pipelines (activation images, weight tiles, TMEM accumulators: 2 buffers) run continuously ACROSS tiles,
@@ -146,7 +148,9 @@ template <bool SIMPLE>
 __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve-up (all image / tile bases 1024-byte aligned)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (pointer arithmetic on the __shared__ array, not integer casts: the compiler must keep the shared address space --
+  //  with the cast it emitted GENERIC ld / st for every image / staging access of the producers and the epilogue)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int img_bytes = p.rows * 128;                 // one plane of one activation stage
   const int a_stage_bytes = 2 * img_bytes;            // hi + lo
   const int b_stage_bytes = 2 * p.NT * 128;           // hi + lo weight tile
@@ -163,7 +167,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   // per-tap image row shift in descriptor units (16 bytes): the MMA issuer reads it with one LDS per tap instead of a
   // dynamically indexed kernel-parameter load (constant-bank miss + address arithmetic on the issuing thread)
   uint32_t* s_tapshift = tmem_slot + 4;          // [kMaxTaps]
-  float* epi_stage = reinterpret_cast<float*>(s_tapshift + kMaxTaps);   // 4 epilogue warps x (32 rows x 32 fp32), 16-byte aligned
+  float* epi_stage = reinterpret_cast<float*>(s_tapshift + kMaxTaps);   // 8 epilogue warps x (32 rows x 16 fp32), 16-byte aligned
+  float* epi_bias = epi_stage + 8 * 32 * 16;                            // 8 epilogue warps x 256 floats
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mtiles = p.ph_mt0[p.nphases];   // m-tiles of all phases (each: 128 flattened outputs m * nsub + w)
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   const uint32_t tmem_acc = *tmem_slot;
   const uint32_t buf_cols = (uint32_t)(p.tmem_cols / 2);
 
-  if (warp < 4 || warp >= 10) {
+  if (warp < 4 || (warp >= 10 && warp < 14)) {
     // ===================== activation producers =====================
     const int pg = warp < 4 ? 0 : 1;                 // producer group: stages it = pg, pg + 2, ...
     const int ptid = warp < 4 ? tid : tid - 320;     // 0..127 inside the group
@@ -206,7 +211,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           rm.base_row = (long long)bb * p.t_in * p.nsub;
           rm.fv0 = f0 + p.grp_qlo[g] * p.nsub;
           rm.nsub = p.nsub; rm.step = p.i_step; rm.rho = p.grp_rho[g]; rm.up = p.up; rm.t_lim = p.t_in * p.up;
-          stage_rows<5, SIMPLE>(img_hi, img_hi + img_bytes, p.in, p.in.p, p.in.aux, p.c_in, ch_base + c * kTcKC,
+          stage_rows<5, SIMPLE, 3>(img_hi, img_hi + img_bytes, p.in, p.in.p, p.in.aux, p.c_in, ch_base + c * kTcKC,
                                 min(kTcKC, p.kg - c * kTcKC), false, rm, p.rows, ptid);
           fence_proxy_async();
           mbar_arrive(&full_a[s]);
@@ -329,34 +334,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
     __syncwarp();
   } else {
-    // ===================== epilogue (warps 6-9; TMEM lane quarter = warp & 3) =====================
-    // tcgen05.ld hands every thread ONE output row (32 fp32 columns per chunk).  Writing rows straight from that layout
-    // makes each 16-byte warp store touch 32 different 128-byte lines (measured: 9 us to drain one 128 x 128 tile, ~2
-    // cycles per line -- LSU-bound, profiles/r02_notes.md).  Instead every warp transposes its 32 x 32 chunk through a
-    // private 4 KB shared-memory tile (16-byte chunks XOR-swizzled by row: conflict-free both ways) so that 8 consecutive
-    // lanes cover one 128-byte row segment: residual / mask loads, the read-modify-write of `accumulate` and the stores
-    // are all fully coalesced (4 lines per warp instruction).  Bias and the output activation are applied before the
-    // transposition (they are per column), residual / derivative masks after it (they are per element).
+    // ===================== epilogue (warps 6-9 and 14-17; TMEM lane quarter = warp & 3) =====================
+    // Two groups of four warps: group e owns the tiles with (ti & 1) == e, i.e. TMEM accumulator buffer e -- a tile's
+    // epilogue is a long, latency-bound instruction stream per warp (~1.7 us per 32-column chunk measured with one
+    // group), so two tiles are drained concurrently.
+    // tcgen05.ld hands every thread ONE output row.  Writing rows straight from that layout makes each 16-byte warp
+    // store touch 32 different 128-byte lines, so every warp transposes 32 rows x 16 columns at a time through a private
+    // 2 KB shared-memory tile (16-byte chunks XOR-swizzled: conflict-free both ways): 4 consecutive lanes then cover one
+    // 64-byte row segment, 8 rows per warp instruction -- residual / mask loads, the read-modify-write of `accumulate`
+    // and the stores are whole 32-byte sectors.  Bias and the output activation are applied before the transposition
+    // (per column), residual / derivative masks after it (per element).
     const int quarter = warp & 3;
-    float* stg = epi_stage + (size_t)quarter * (32 * 32);
+    const int egrp = warp >= 14 ? 1 : 0;
+    const int ewarp = egrp * 4 + quarter;
+    float* stg = epi_stage + (size_t)ewarp * (32 * 16);
+    float* sbias = epi_bias + ewarp * 256;          // this warp's copy of the tile's bias (NT <= 256 floats)
+    const bool tracer = (tid == 192 || tid == 448);
     int ti = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      if ((ti & 1) != egrp) continue;
       const int gm = tile % mtiles, nt = (tile / mtiles) % p.ntiles, bb = tile / (mtiles * p.ntiles);
       int ph = 0;
       while (gm >= p.ph_mt0[ph + 1]) ++ph;
       const int mt = gm - p.ph_mt0[ph];
       const int F = p.ph_M[ph] * p.nsub;
       const int buf = ti & 1;
-      if (tid == 192) trace_ev(p, 3, ti, 0);
+      if (tracer) trace_ev(p, 3, ti, 0);
       mbar_wait(&tmem_full[buf], (ti >> 1) & 1);
       tc_fence_after();
-      if (tid == 192) trace_ev(p, 3, ti, 1);
+      if (tracer) trace_ev(p, 3, ti, 1);
       const int f = mt * kTcM + quarter * 32 + lane;
       const bool valid = f < F;
       const int m = valid ? (p.nsub == 1 ? f : f / p.nsub) : 0;
       const int w = valid ? f - m * p.nsub : 0;
       const int to = p.ph_ooff[ph] + p.o_step * m;
-      const long long obase = (((long long)bb * p.t_out + to) * p.nsub + w) * p.c_out + (long long)nt * p.n_stride;
+      const int orow = (bb * p.t_out + to) * p.nsub + w;                  // output row (flattened), < 2^31
+      const long long obase = (long long)orow * p.c_out + (long long)nt * p.n_stride;
       const int n_valid = min(p.n_stride, p.c_out - nt * p.n_stride);   // real output channels of this tile
       const bool vec_out = SIMPLE || ((n_valid | p.c_out | p.n_stride) & 3) == 0;
       const uint32_t t_lane = tmem_acc + (uint32_t)buf * buf_cols + ((uint32_t)(quarter * 32) << 16);
@@ -364,21 +377,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       const float* side_p = p.resid ? p.resid : p.mask.p;
       const bool side_is_mask = p.resid == nullptr;
       const bool coalesced = vec_out && !(p.resid && p.mask.p);          // warp-uniform
-      // rows this lane serves in the coalesced phase: row_i = 4 * i + lane / 8 (i = 0..7), 16-byte chunk lane % 8
-      long long rbase[8];
+      if (coalesced && p.bias) {   // per-tile bias -> shared memory once: the chunk loop reads it with broadcast LDS.128
+        __syncwarp();
+        for (int e = lane; e < p.NT; e += 32) sbias[e] = e < n_valid ? __ldg(p.bias + nt * p.n_stride + e) : 0.f;
+        __syncwarp();
+      }
+      // rows this lane serves in the coalesced phase: row_i = 8 * i + lane / 4 (i = 0..3), 16-byte chunk cq = lane % 4
+      const int cq = lane & 3;
+      float* rptr[4];                      // &out[row_i][first column of this lane's 16-byte chunk in this tile]
       uint32_t rok = 0;
       if (coalesced) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int src = i * 4 + (lane >> 3);
-          rbase[i] = __shfl_sync(0xffffffffu, obase, src);
+        for (int i = 0; i < 4; ++i) {
+          const int src = i * 8 + (lane >> 2);
+          rptr[i] = p.out + ((long long)__shfl_sync(0xffffffffu, orow, src) * p.c_out + (long long)nt * p.n_stride + cq * 4);
           rok |= (uint32_t)__shfl_sync(0xffffffffu, (int)valid, src) << i;
         }
       }
+      // residual / mask tensors are indexed like the output: one pointer difference serves every element
+      const long long side_delta = side_p ? side_p - p.out : 0;
+      const int side_kind = !side_p ? 0 : (!side_is_mask ? 1 : 2);          // 0 none, 1 residual add, 2 act' mask
       for (int n0 = 0; n0 < p.NT; n0 += 32) {
         uint32_t rr[32];
-        if (tid == 192 && ti < 2) trace_ev(p, 4 + ti, n0 >> 5, 0);   // roles 4 / 5: per-chunk stamps of epilogue warp 0, tiles 0 / 1
-        if (p.NT - n0 >= 32) {
+        if (tracer && ti < 2) trace_ev(p, 4 + ti, n0 >> 5, 0);   // roles 4 / 5: per-chunk stamps, tiles 0 / 1
+        if (p.dbg & 8) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) rr[e] = (uint32_t)(e + lane);
+        } else if (p.NT - n0 >= 32) {
           tmem_ld32(t_lane + (uint32_t)n0, rr);
         } else {  // NT % 32 == 16
           uint32_t r16[16];
@@ -387,18 +412,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           for (int e = 0; e < 16; ++e) { rr[e] = r16[e]; rr[16 + e] = 0u; }
         }
         const int ncols_t = min(32, n_valid - n0);       // real columns of this chunk (tile-uniform, may be <= 0)
-        // side-tensor loads are issued before the TMEM load is waited for (coalesced: this lane's 8 (row, chunk) cells)
-        const int cq = lane & 7;
-        const bool col_ok = cq * 4 < ncols_t;
-        float4 sd[8];
-        if (coalesced && side_p) {
+        // side-tensor loads of the first 16-column half are issued before the TMEM load is waited for; those of the
+        // second half while the first half is being transposed (volatile asm: the compiler must not sink them to their
+        // uses -- that serialised the store loop on one L2 round trip per row group)
+        float4 sd[2][4];
+        auto side_load = [&](int h) {
+          const bool col_ok = h * 16 + cq * 4 < ncols_t;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            sd[i] = (col_ok && ((rok >> i) & 1u)) ? __ldg(reinterpret_cast<const float4*>(side_p + rbase[i] + n0 + cq * 4))
-                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+          for (int i = 0; i < 4; ++i) {
+            const float* a = (col_ok && ((rok >> i) & 1u)) ? rptr[i] + side_delta + (n0 + h * 16) : side_p;
+            asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(sd[h][i].x), "=f"(sd[h][i].y), "=f"(sd[h][i].z), "=f"(sd[h][i].w) : "l"(a));
+          }
+        };
+        if (coalesced && side_p && !(p.dbg & 1)) side_load(0);
         tmem_ld_wait();
-        if (p.fuse2) {   // + the hi*lo products (columns [NT, 2*NT)), 16 columns at a time (registers)
+        if (p.fuse2 && !(p.dbg & 8)) {   // + the hi*lo products (columns [NT, 2*NT)), 16 columns at a time (registers)
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t t2[16];
@@ -411,58 +440,62 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         if (n0 + 32 >= p.NT) {   // last TMEM read of this tile: hand the buffer back to the MMA issuer
           tc_fence_before();
           mbar_arrive(&tmem_empty[buf]);
-          if (tid == 192) trace_ev(p, 3, ti, 2);
+          if (tracer) trace_ev(p, 3, ti, 2);
         }
-        if (tid == 192 && ti < 2) trace_ev(p, 4 + ti, n0 >> 5, 1);
-        if (coalesced) {
-          // ---- row-owner layout: bias + output activation, then into the transposition tile
+        if (tracer && ti < 2) trace_ev(p, 4 + ti, n0 >> 5, 1);
+        if (coalesced && !(p.dbg & 4)) {
 #pragma unroll
-          for (int e8 = 0; e8 < 8; ++e8) {
-            const int e = e8 * 4;
-            float v[4] = {__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3])};
-            if (p.bias && e < ncols_t) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + nt * p.n_stride + n0 + e));
-              v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+          for (int h = 0; h < 2; ++h) {
+            if (h == 0 && side_p && !(p.dbg & 1)) side_load(1);
+            // ---- row-owner layout: bias + output activation, then into the transposition tile
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const int e = h * 16 + e4 * 4;
+              float v[4] = {__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3])};
+              if (p.bias) {
+                const float4 b = *reinterpret_cast<const float4*>(sbias + n0 + e);
+                v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+              }
+              if (p.out_act == KT_ACT_LRELU) {
+#pragma unroll
+                for (int z = 0; z < 4; ++z) v[z] = v[z] > 0.f ? v[z] : v[z] * p.out_slope;
+              } else if (!SIMPLE && p.out_act == KT_ACT_TANH) {
+#pragma unroll
+                for (int z = 0; z < 4; ++z) v[z] = tanhf(v[z]);
+              }
+              *reinterpret_cast<float4*>(stg + lane * 16 + ((e4 ^ ((lane >> 1) & 3)) << 2)) = make_float4(v[0], v[1], v[2], v[3]);
             }
-            if (p.out_act == KT_ACT_LRELU) {
+            __syncwarp();
+            // ---- coalesced layout: 4 lanes = one 64-byte row segment, 8 rows per instruction
+            const bool col_ok = h * 16 + cq * 4 < ncols_t;
 #pragma unroll
-              for (int z = 0; z < 4; ++z) v[z] = v[z] > 0.f ? v[z] : v[z] * p.out_slope;
-            } else if (!SIMPLE && p.out_act == KT_ACT_TANH) {
-#pragma unroll
-              for (int z = 0; z < 4; ++z) v[z] = tanhf(v[z]);
-            }
-            *reinterpret_cast<float4*>(stg + lane * 32 + ((e8 ^ (lane & 7)) << 2)) = make_float4(v[0], v[1], v[2], v[3]);
-          }
-          __syncwarp();
-          if (tid == 192 && ti < 2) trace_ev(p, 4 + ti, n0 >> 5, 2);
-          // ---- coalesced layout: 8 lanes = one 128-byte row segment
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int row = i * 4 + (lane >> 3);
-            const float4 t = *reinterpret_cast<const float4*>(stg + row * 32 + ((cq ^ (row & 7)) << 2));
-            float v[4] = {t.x, t.y, t.z, t.w};
-            if (side_p) {
-              const float4 a = sd[i];
-              if (side_is_mask) {
-                v[0] = side_apply(v[0], a.x, p.mask.mode, p.mask.slope);
-                v[1] = side_apply(v[1], a.y, p.mask.mode, p.mask.slope);
-                v[2] = side_apply(v[2], a.z, p.mask.mode, p.mask.slope);
-                v[3] = side_apply(v[3], a.w, p.mask.mode, p.mask.slope);
-              } else {
-                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+            for (int i = 0; i < 4; ++i) {
+              const int row = i * 8 + (lane >> 2);
+              float4 t = *reinterpret_cast<const float4*>(stg + row * 16 + ((cq ^ ((row >> 1) & 3)) << 2));
+              const float4 a = sd[h][i];
+              if (side_kind == 1) {
+                t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+              } else if (side_kind == 2) {
+                if (p.mask.mode == SIDE_DLRELU) {
+                  t.x = a.x > 0.f ? t.x : t.x * p.mask.slope; t.y = a.y > 0.f ? t.y : t.y * p.mask.slope;
+                  t.z = a.z > 0.f ? t.z : t.z * p.mask.slope; t.w = a.w > 0.f ? t.w : t.w * p.mask.slope;
+                } else {
+                  t.x = side_apply(t.x, a.x, p.mask.mode, p.mask.slope); t.y = side_apply(t.y, a.y, p.mask.mode, p.mask.slope);
+                  t.z = side_apply(t.z, a.z, p.mask.mode, p.mask.slope); t.w = side_apply(t.w, a.w, p.mask.mode, p.mask.slope);
+                }
+              }
+              if (col_ok && ((rok >> i) & 1u) && !(p.dbg & 2)) {
+                float* o = rptr[i] + (n0 + h * 16);
+                if (!SIMPLE && p.accumulate) {
+                  const float4 c = *reinterpret_cast<const float4*>(o);
+                  t.x += c.x; t.y += c.y; t.z += c.z; t.w += c.w;
+                }
+                *reinterpret_cast<float4*>(o) = t;
               }
             }
-            if (col_ok && ((rok >> i) & 1u)) {
-              float* o = p.out + rbase[i] + n0 + cq * 4;
-              if (!SIMPLE && p.accumulate) {
-                const float4 a = *reinterpret_cast<const float4*>(o);
-                v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
-              }
-              *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-            }
+            __syncwarp();      // the tile is rewritten by the next half
           }
-          __syncwarp();      // the tile is rewritten by the next chunk
-          if (tid == 192 && ti < 2) trace_ev(p, 4 + ti, n0 >> 5, 3);
+          if (tracer && ti < 2) trace_ev(p, 4 + ti, n0 >> 5, 3);
         } else if (!SIMPLE && valid) {
           // thin / unaligned tiles (C_out = 1, ...): scalar epilogue
           const int ncols = max(ncols_t, 0);
@@ -479,7 +512,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           }
         }
       }
-      if (tid == 192) trace_ev(p, 3, ti, 3);
+      if (tracer) trace_ev(p, 3, ti, 3);
     }
   }
 
@@ -506,6 +539,18 @@ struct TcLayerPlan {
   int ntiles, kchunks, grouped;
   int kin_g, pout_g;   // grouped: channels of ONE group on the contraction / produced side (kg = gt * kin_g)
 };
+
+std::vector<Phase> conv_phases(const KtConv1dDesc* d, int dir);  // conv_ffma.cu
+struct TcParams;
+static int plan_max_rows(const KtConv1dDesc* d, int dir);
+
+// shared memory outside the activation / weight stages: barriers, TMEM slot, tap-shift table, epilogue transposition
+// + bias tiles (see the carve-up in conv_tc_kernel)
+static int tc_fixed_smem(int slots) { return (2 * 3 + 2 * std::max(6, slots) + 4) * 8 + 16 + kMaxTaps * 4 + 8 * 2048 + 8 * 1024; }
+// can a (rows, NT) tiling run with at least two activation and two weight stages?
+static bool tc_ring_fits(int rows, int NT) {
+  return 2 * (2 * rows * 128) + 2 * (2 * NT * 128) <= kMaxDynSmem - 1024 - tc_fixed_smem(0);
+}
 
 static TcLayerPlan layer_plan(const KtConv1dDesc* d, int dir) {
   TcLayerPlan L{};
@@ -537,13 +582,12 @@ static TcLayerPlan layer_plan(const KtConv1dDesc* d, int dir) {
     if (L.NT == 0) return L;
     const long long mtiles = (long long)ceil_div((dir == 0 ? d->t_out : d->t_in) * d->nsub, kTcM) * d->batch;
     if (L.NT == 256 && mtiles * (pout / 256) < 120) L.NT = 128;
+    if (L.NT == 256 && !tc_ring_fits(plan_max_rows(d, dir), 256)) L.NT = 128;   // long-halo (strided) layers: 64 KB weight stages do not fit
     L.n_stride = L.NT; L.ntiles = pout / L.NT;
   }
   L.ok = true;
   return L;
 }
-
-std::vector<Phase> conv_phases(const KtConv1dDesc* d, int dir);  // conv_ffma.cu
 
 // Append one phase (its residue groups and taps) to the launch parameters.  Returns false when the
 // phase does not fit the kernel's limits.  Call reset_phases() first.
@@ -612,6 +656,15 @@ static bool plan_launches(const std::vector<Phase>& phases, int nsub, std::vecto
   return true;
 }
 
+// image rows (128 + halo) the layer's phases need (0: the phases do not fit the kernel's limits)
+static int plan_max_rows(const KtConv1dDesc* d, int dir) {
+  std::vector<TcParams> launches;
+  if (!plan_launches(conv_phases(d, dir), d->nsub, launches, TcParams{})) return 0;
+  int rows = 0;
+  for (const TcParams& lp : launches) rows = std::max(rows, lp.rows);
+  return rows;
+}
+
 // Is (direction dir: 0 fwd, 1 bwd_data) of this layer runnable on the tcgen05 kernel?  -> N tile or 0
 bool thin_cin1_ok(const KtConv1dDesc* d);   // thin.cu
 
@@ -654,18 +707,21 @@ static int sm_count() {
 }
 
 static long long* g_trace = nullptr;   // development aid, not thread-safe: set by kt_debug_set_trace
+static int g_dbg = 0;
+void debug_set_flags(int f) { g_dbg = f; }
 void debug_set_trace(long long* dev_buf) { g_trace = dev_buf; }
 
 static int run_tc(TcParams p, cudaStream_t st) {   // p: phases already planned by plan_launches
   p.trace = g_trace;
-  p.fuse2 = (p.NT <= 128 && p.NT % 32 == 0) ? 1 : 0;
+  p.dbg = g_dbg;
+  p.fuse2 = (p.NT <= 64 && p.NT % 32 == 0) ? 1 : 0;   // NT = 128: same MMA floor either way (192 cycles per K slice), half the TMEM reads in the epilogue
   p.tmem_cols = 32;
   while (p.tmem_cols < (p.fuse2 ? 2 : 1) * p.NT) p.tmem_cols <<= 1;
   p.tmem_cols *= 2;                                   // two accumulator buffers
   const int a_stage = 2 * p.rows * 128;
   const int b_stage = 2 * p.NT * 128;
   const int slots = p.ntaps * p.kchunks;                                      // weight tiles of the whole layer
-  const int bar_bytes = (2 * 3 + 2 * std::max(6, slots) + 4) * 8 + 16 + kMaxTaps * 4 + 4 * 4096;   // barriers, TMEM slot, tap-shift table, epilogue transposition tiles
+  const int bar_bytes = tc_fixed_smem(slots);
   const int budget = kMaxDynSmem - 1024 /*align slack*/ - bar_bytes;
   p.w_resident = 0;
   if (p.ntiles == 1 && slots <= 160 && 2 * a_stage + slots * b_stage <= budget) {

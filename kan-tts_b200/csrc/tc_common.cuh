@@ -50,10 +50,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trap (launch error), never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a trap (launch error), never as a hung GPU.  The try_wait carries CUTLASS's
+// suspend-time hint (the hardware parks the warp instead of polling) and the loop must NOT be unrolled: nvcc unrolled it
+// 64x at every call site (~2 KB of SASS each, ~15 sites per kernel), and four concurrently running warp roles were
+// thrashing the instruction cache (stall_no_inst, profiles/r02_notes.md).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spin = 0; spin < (1u << 28); ++spin)
-    if (mbar_try_wait(bar, parity)) return;
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(0x989680u)
+        : "memory");
+    if (ok) return;
+  }
   __trap();
 }
 
@@ -290,7 +304,7 @@ __device__ __forceinline__ void stage_rows_impl(uint8_t* img_hi, uint8_t* img_lo
 // SIMPLE: the host guarantees nsub == 1, up == 1 and 16-byte-aligned 8-channel chunks (c_valid % 8 == 0, c_total % 4
 // == 0): only the vectorised instantiations exist in that kernel variant, which roughly halves its code size -- the
 // generic kernel (~140 KB of SASS shared by four concurrently running warp roles) does not fit the instruction cache.
-template <int NB, bool SIMPLE = false>
+template <int NB, bool SIMPLE = false, int NB_AUX = NB>
 __device__ __forceinline__ void stage_rows(uint8_t* img_hi, uint8_t* img_lo, const Side& s, const float* base,
                                            const float* aux_base, int c_total, int ch0, int c_valid, bool fill_all,
                                            const RowMap& rm, int rows, int tid) {
@@ -304,12 +318,12 @@ __device__ __forceinline__ void stage_rows(uint8_t* img_hi, uint8_t* img_lo, con
   const bool vec = nv == 8 && (c_total & 3) == 0 && ((ch0 + q * 8) & 3) == 0;
   const bool has_aux = s.mode >= SIDE_DLRELU;
   if constexpr (SIMPLE) {
-    if (has_aux) stage_rows_impl<NB, true, true, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
+    if (has_aux) stage_rows_impl<NB_AUX, true, true, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
     else stage_rows_impl<NB, true, false, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
     return;
   }
   if (vec) {
-    if (has_aux) stage_rows_impl<NB, true, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
+    if (has_aux) stage_rows_impl<NB_AUX, true, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
     else stage_rows_impl<NB, true, false>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
   } else {
     if (has_aux) stage_rows_impl<2, false, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);

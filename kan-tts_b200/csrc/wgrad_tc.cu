@@ -58,7 +58,9 @@ struct WgTcParams {
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (pointer arithmetic on the __shared__ array, not integer casts: the compiler must keep the shared address space --
+  //  with the cast it emitted GENERIC ld / st for every image / staging access of the producers and the epilogue)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   const int img_a = p.rows_a * 128;            // one plane of one A image
   const int img_b = kWgTK * 128;               // one plane of one B image
   const int stage_bytes = 2 * (p.a_groups * img_a + p.b_groups * img_b);

@@ -252,8 +252,17 @@ class ResidualBlock(nn.Module):
 
     def forward_rows(self, x):
         for c1, c2 in zip(self.convs1, self.convs2):
-            xt = c1.forward_rows(x)
-            x = c2.forward_rows(xt, resid=x)
+            n1, n2 = c1.conv1d, c2.conv1d
+            rd = ops.resblock_desc(n1.spec, n2.spec, x.shape[0], x.shape[1]) \
+                if (ops._FUSE_RESBLOCK and not ops._FORCE_FFMA and x.dim() == 3 and n1.norm != "spectral" and n2.norm != "spectral") else None
+            if rd is not None:
+                # thin stages (32 / 64 channels): the pair is ONE launch, the intermediate stays on the SM (kt_resblock_fwd)
+                v1, g1 = n1.effective_weight()
+                v2, g2 = n2.effective_weight()
+                x = ops.resblock(x, n1.spec, n1._cache, v1, g1, n1.bias, n2.spec, n2._cache, v2, g2, n2.bias, rd)
+            else:
+                xt = c1.forward_rows(x)
+                x = c2.forward_rows(xt, resid=x)
         return x
 
     def forward(self, x):

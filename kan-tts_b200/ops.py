@@ -12,8 +12,8 @@ from dataclasses import dataclass, field
 import torch
 
 from . import _lib
-from ._lib import (KT_ACT_LRELU, KT_ACT_NONE, KT_ACT_TANH, KT_PATH_AUTO, KT_PATH_FFMA, KT_PATH_TC, KtConv1dDesc, KtMelDesc, check, ptr,
-                   stream_ptr)
+from ._lib import (KT_ACT_LRELU, KT_ACT_NONE, KT_ACT_TANH, KT_PATH_AUTO, KT_PATH_FFMA, KT_PATH_TC, KtConv1dDesc, KtMelDesc,
+                   KtResblockDesc, check, ptr, stream_ptr)
 
 _launches = 0          # kernels-launched counter (bench.py reports it as gpu_launches)
 
@@ -367,6 +367,76 @@ def _tc_tile(lib, spec, d, direction):
     return nt
 
 
+def _weight_backward(spec, d, x_, dy, y_, v, g, params, norm, need_v, need_g, need_b):
+    """Weight-gradient chain of one conv layer (wgrad kernel -> split-K reduce -> bias column sums -> weight-norm backward),
+    shared by ConvFn.backward and ResblockFn.backward.  x_, dy, y_: the layer's input, output gradient and (when it has a
+    fused output activation) output, already restricted to the batch items that carry gradient.  -> (dbias, dv, dg): the
+    gradients to hand to autograd, None for parameters whose .grad the kernels accumulated into directly (mark_direct_grad)."""
+    global _tc_launches
+    dbias = dv = dg = None
+    need_w = need_v or need_g
+    if not (need_w or need_b):
+        return dbias, dv, dg
+    lib = _lib.load()
+    has_g = g is not None
+    pv, pg, pb = params
+    direct = (need_w and pv.is_leaf and _is_direct(pv) and _is_direct(pg) and (not need_b or _is_direct(pb))
+              and need_v and (not has_g or need_g))
+    side = _wgrad_stream(x_.device, pv) if (direct and _WGRAD_ASYNC) else None
+    st = stream_ptr()
+    if side is not None:
+        # nothing of this chain is handed back to autograd (the kernels accumulate into param.grad), so it
+        # runs on a side stream; join_wgrad_streams() orders it before the optimizer
+        side.wait_stream(torch.cuda.current_stream())
+        for t in (x_, dy, y_):
+            if t is not None:
+                t.record_stream(side)
+        cm = torch.cuda.stream(side)
+        cm.__enter__()
+        st = stream_ptr()
+    try:
+        dw = torch.empty(spec.w_numel, device=x_.device, dtype=torch.float32)
+        if need_b:
+            dbias = torch.empty(spec.c_out, device=x_.device, dtype=torch.float32)
+        ws_floats = _wgrad_tc_workspace(lib, spec, d)
+        if ws_floats:
+            ws = torch.empty(ws_floats, device=x_.device, dtype=torch.float32)
+            with _timed("conv_wgrad_tc", spec, d):
+                check(lib.kt_conv1d_bwd_weight_tc(ctypes.byref(d), ptr(x_), ptr(dy), ptr(y_), ptr(dw), ptr(dbias),
+                                                  ptr(ws), ws_floats, st), "kt_conv1d_bwd_weight_tc")
+            _tc_launches += 1
+        else:
+            with _timed("conv_wgrad_ffma", spec, d):
+                check(lib.kt_conv1d_bwd_weight(ctypes.byref(d), ptr(x_), ptr(dy), ptr(y_), ptr(dw), ptr(dbias), st),
+                      "kt_conv1d_bwd_weight")
+        _count(4 if need_b else 2)
+        if need_w:
+            vd = v.detach().contiguous()
+            gd = None if g is None else g.detach().contiguous()
+            mode = 1 if has_g else 0
+            if direct:
+                # AccumulateGrad folded into the kernel: param.grad += (train.FlatGrads buffers, pre-zeroed)
+                check(lib.kt_weight_grad_accum(ptr(dw), ptr(vd), ptr(gd), ptr(norm), None, mode, vd.shape[0],
+                                               vd.shape[1], spec.kernel, int(spec.transposed), spec.groups,
+                                               ptr(pv.grad), None if pg is None else ptr(pg.grad),
+                                               ptr(dbias) if need_b else None,
+                                               ptr(pb.grad) if need_b else None, spec.c_out if need_b else 0, st),
+                      "kt_weight_grad_accum")
+                dbias = None
+            else:
+                dv = torch.empty_like(vd)
+                if has_g:
+                    dg = torch.empty_like(g)
+                check(lib.kt_weight_grad(ptr(dw), ptr(vd), ptr(gd), ptr(norm), None, mode, vd.shape[0],
+                                         vd.shape[1], spec.kernel, int(spec.transposed), spec.groups, ptr(dv),
+                                         ptr(dg), st), "kt_weight_grad")
+            _count()
+    finally:
+        if side is not None:
+            cm.__exit__(None, None, None)
+    return dbias, dv, dg
+
+
 class ConvFn(torch.autograd.Function):
     """y = act_out(conv(act_in(x)) + bias) + resid   on channels-last rows."""
 
@@ -463,68 +533,128 @@ class ConvFn(torch.autograd.Function):
             _count(max(spec.stride if not spec.transposed else 1, spec.upsample))
         if ctx.has_resid and ctx.needs_input_grad[1]:
             dres = dy_full
-        need_w = ctx.needs_input_grad[3] or (ctx.has_g and ctx.needs_input_grad[4])
-        need_b = ctx.has_bias and ctx.needs_input_grad[2]
-        if need_w or need_b:
-            pv, pg, pb = ctx.params
-            direct = (need_w and pv.is_leaf and _is_direct(pv) and _is_direct(pg) and (not need_b or _is_direct(pb))
-                      and ctx.needs_input_grad[3] and (not ctx.has_g or ctx.needs_input_grad[4]))
-            side = _wgrad_stream(x.device, pv) if (direct and _WGRAD_ASYNC) else None
-            if side is not None:
-                # nothing of this chain is handed back to autograd (the kernels accumulate into param.grad), so it
-                # runs on a side stream; join_wgrad_streams() orders it before the optimizer
-                side.wait_stream(torch.cuda.current_stream())
-                for t in (x_, dy, y_):
-                    if t is not None:
-                        t.record_stream(side)
-                cm = torch.cuda.stream(side)
-                cm.__enter__()
-                st = stream_ptr()
-            try:
-                dw = torch.empty(spec.w_numel, device=x.device, dtype=torch.float32)
-                if need_b:
-                    dbias = torch.empty(spec.c_out, device=x.device, dtype=torch.float32)
-                ws_floats = _wgrad_tc_workspace(lib, spec, d)
-                if ws_floats:
-                    ws = torch.empty(ws_floats, device=x.device, dtype=torch.float32)
-                    with _timed("conv_wgrad_tc", spec, d):
-                        check(lib.kt_conv1d_bwd_weight_tc(ctypes.byref(d), ptr(x_), ptr(dy), ptr(y_), ptr(dw), ptr(dbias),
-                                                          ptr(ws), ws_floats, st), "kt_conv1d_bwd_weight_tc")
-                    _tc_launches += 1
-                else:
-                    with _timed("conv_wgrad_ffma", spec, d):
-                        check(lib.kt_conv1d_bwd_weight(ctypes.byref(d), ptr(x_), ptr(dy), ptr(y_), ptr(dw), ptr(dbias), st),
-                              "kt_conv1d_bwd_weight")
-                _count(4 if need_b else 2)
-                if need_w:
-                    vd = v.detach().contiguous()
-                    gd = None if g is None else g.detach().contiguous()
-                    mode = 1 if ctx.has_g else 0
-                    if direct:
-                        # AccumulateGrad folded into the kernel: param.grad += (train.FlatGrads buffers, pre-zeroed)
-                        check(lib.kt_weight_grad_accum(ptr(dw), ptr(vd), ptr(gd), ptr(ctx.norm), None, mode, vd.shape[0],
-                                                       vd.shape[1], spec.kernel, int(spec.transposed), spec.groups,
-                                                       ptr(pv.grad), None if pg is None else ptr(pg.grad),
-                                                       ptr(dbias) if need_b else None,
-                                                       ptr(pb.grad) if need_b else None, spec.c_out if need_b else 0, st),
-                              "kt_weight_grad_accum")
-                        dbias = None
-                    else:
-                        dv = torch.empty_like(vd)
-                        if ctx.has_g:
-                            dg = torch.empty_like(g)
-                        check(lib.kt_weight_grad(ptr(dw), ptr(vd), ptr(gd), ptr(ctx.norm), None, mode, vd.shape[0],
-                                                 vd.shape[1], spec.kernel, int(spec.transposed), spec.groups, ptr(dv),
-                                                 ptr(dg), st), "kt_weight_grad")
-                    _count()
-            finally:
-                if side is not None:
-                    cm.__exit__(None, None, None)
+        dbias, dv, dg = _weight_backward(spec, d, x_, dy, y_, v, g, ctx.params, ctx.norm, ctx.needs_input_grad[3],
+                                         ctx.has_g and ctx.needs_input_grad[4], ctx.has_bias and ctx.needs_input_grad[2])
         return dx, dres, dbias, dv, dg, None, None
 
 
 def conv(x, spec, cache, v, g=None, bias=None, resid=None):
     return ConvFn.apply(x, resid, bias, v, g, spec, cache)
+
+
+# ---- fused ResidualBlock unit (csrc/resblock_tc.cu) -------------------------------------------------------------------
+_FUSE_RESBLOCK = os.environ.get("KANTTS_B200_FUSE_RESBLOCK", "1") != "0"
+
+
+def set_fuse_resblock(flag):
+    """Route the (convs1[i], convs2[i]) pairs of the thin generator stages through the fused kernel (default) or through
+    two conv launches (A/B testing)."""
+    global _FUSE_RESBLOCK
+    _FUSE_RESBLOCK = bool(flag)
+
+
+def resblock_desc(spec1, spec2, batch, t):
+    """-> KtResblockDesc when the pair (dilated conv, dilation-1 conv; same channels / kernel; fused input LeakyReLU, no
+    output activation) can run on the fused kernel for this shape, else None.  Cached per shape on spec1."""
+    key = ("rb", batch, t)
+    d = spec1._descs.get(key, False)
+    if d is not False:
+        return d
+    d = None
+    ok = (spec1.c_in == spec1.c_out == spec2.c_in == spec2.c_out and spec1.kernel == spec2.kernel and spec2.dilation == 1
+          and spec1.stride == spec2.stride == 1 and spec1.groups == spec2.groups == 1 and not spec1.transposed
+          and not spec2.transposed and spec1.upsample == spec2.upsample == 1 and spec1.act_in == spec2.act_in == KT_ACT_LRELU
+          and spec1.act_in_slope == spec2.act_in_slope and spec1.act_out == spec2.act_out == KT_ACT_NONE
+          and spec1.t_out(t) == t and spec2.t_out(t) == t and spec1.path != KT_PATH_FFMA and spec2.path != KT_PATH_FFMA)
+    if ok:
+        cand = KtResblockDesc(batch=batch, t=t, channels=spec1.c_in, kernel=spec1.kernel, dilation=spec1.dilation,
+                              pad_left1=spec1.pad_left, pad_left2=spec2.pad_left, slope=spec1.act_in_slope, path=KT_PATH_AUTO)
+        if _lib.load().kt_resblock_plan(ctypes.byref(cand)) == 1:
+            d = cand
+    spec1._descs[key] = d
+    return d
+
+
+def _rb_image(pw, rd):
+    """the fused kernel's weight image of one conv (kt_resblock_pack), cached beside the tcgen05 tile images"""
+    k = ("rb", rd.channels, rd.kernel)
+    img = pw.img.get(k)
+    if img is None or k in pw.img_stale:
+        lib = _lib.load()
+        if img is None:
+            img = torch.empty(int(lib.kt_resblock_image_bytes(ctypes.byref(rd))) // 2, device=pw.w_fwd.device, dtype=torch.bfloat16)
+            pw.img[k] = img
+        check(lib.kt_resblock_pack(ctypes.byref(rd), ptr(pw.w_fwd), ptr(img, True), stream_ptr()), "kt_resblock_pack")
+        _count()
+        pw.img_stale.discard(k)
+    return img
+
+
+class ResblockFn(torch.autograd.Function):
+    """y = x + c2(lrelu(c1(lrelu(x)) + b1)) + b2  (layers.py:213-220) in ONE launch; backward = kt_resblock_bwd (both data
+    gradients) + the two convs' weight-gradient chains, from the saved (x, h)."""
+
+    @staticmethod
+    def forward(ctx, x, b1, v1, g1, b2, v2, g2, spec1, cache1, spec2, cache2, rd):
+        global _tc_launches
+        lib = _lib.load()
+        x = x.contiguous()
+        B, T = x.shape[0], x.shape[1]
+        pw1 = prepare_weight(cache1, spec1, v1, g1)
+        pw2 = prepare_weight(cache2, spec2, v2, g2)
+        img1, img2 = _rb_image(pw1, rd), _rb_image(pw2, rd)
+        need_grad = any(ctx.needs_input_grad[:7])
+        y = torch.empty_like(x)
+        h = torch.empty_like(x) if need_grad else None
+        with _timed("resblock_fwd_tc", spec1, spec1.desc(B, 1, T)):
+            check(lib.kt_resblock_fwd(ctypes.byref(rd), ptr(x), ptr(img1, True), ptr(None if b1 is None else b1.detach()),
+                                      ptr(img2, True), ptr(None if b2 is None else b2.detach()), ptr(h), ptr(y), stream_ptr()),
+                  "kt_resblock_fwd")
+        _tc_launches += 1
+        _count()
+        if need_grad:
+            nb = B if _grad_items is None else min(_grad_items, B)
+            d1, d2 = spec1.desc(nb, 1, T), spec2.desc(nb, 1, T)
+            ctx.nb, ctx.d1, ctx.d2, ctx.specs = nb, d1, d2, (spec1, spec2)
+            nt1, nt2 = _tc_tile(lib, spec1, d1, 1), _tc_tile(lib, spec2, d2, 1)
+            assert nt1 and nt2, "fused resblock: the data gradients run on the tcgen05 kernels"
+            ctx.img_bwd = (pw1.tc_image(spec1, d1, 1, nt1), pw2.tc_image(spec2, d2, 1, nt2))
+            ctx.norms = (pw1.norm, pw2.norm)
+            ctx.params = ((v1, g1, b1), (v2, g2, b2))
+            ctx.save_for_backward(x, h, v1, g1, v2, g2)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        global _tc_launches
+        lib = _lib.load()
+        x, h, v1, g1, v2, g2 = ctx.saved_tensors
+        spec1, spec2 = ctx.specs
+        dy = dy.contiguous()
+        dy_full = dy
+        if ctx.nb < x.shape[0]:
+            x_, h_, dy = x[:ctx.nb], h[:ctx.nb], dy[:ctx.nb]
+        else:
+            x_, h_ = x, h
+        dh = torch.empty_like(x_)
+        dx = torch.empty_like(x)
+        with _timed("conv_dgrad_tc", spec1, ctx.d1):
+            check(lib.kt_resblock_bwd(ctypes.byref(ctx.d1), ctypes.byref(ctx.d2), ptr(x_), ptr(h_), ptr(dy), ptr(ctx.img_bwd[0], True),
+                                      ptr(ctx.img_bwd[1], True), ptr(dh), ptr(dx if ctx.nb == x.shape[0] else dx[:ctx.nb]),
+                                      stream_ptr()), "kt_resblock_bwd")
+        _tc_launches += 2
+        _count(3)
+        ni = ctx.needs_input_grad
+        (pv1, pg1, pb1), (pv2, pg2, pb2) = ctx.params
+        db2, dv2, dg2 = _weight_backward(spec2, ctx.d2, h_, dy, None, v2, g2, (pv2, pg2, pb2), ctx.norms[1], ni[5],
+                                         g2 is not None and ni[6], pb2 is not None and ni[4])
+        db1, dv1, dg1 = _weight_backward(spec1, ctx.d1, x_, dh, None, v1, g1, (pv1, pg1, pb1), ctx.norms[0], ni[2],
+                                         g1 is not None and ni[3], pb1 is not None and ni[1])
+        return (dx if ni[0] else None), db1, dv1, dg1, db2, dv2, dg2, None, None, None, None, None
+
+
+def resblock(x, spec1, cache1, v1, g1, b1, spec2, cache2, v2, g2, b2, rd):
+    return ResblockFn.apply(x, b1, v1, g1, b2, v2, g2, spec1, cache1, spec2, cache2, rd)
 
 
 class SinAddFn(torch.autograd.Function):

@@ -1,5 +1,5 @@
 """gpurun_out/launchesNN.csv (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv)
--> profiles/r01_launches_step_runNN.md (per-kernel table) + profiles/traffic.json (DRAM bytes per launch by kernel class)."""
+-> profiles/r02_launches_step_runNN.md (per-kernel table) + profiles/traffic.json (DRAM bytes per launch by kernel class)."""
 import collections, csv, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 src, tag = sys.argv[1], sys.argv[2]
@@ -29,7 +29,7 @@ out = [f"# ncu launch list, one C2 train step ({tag})", "",
        "| ms | share | launches | avg us | DRAM read MB | DRAM write MB | kernel |", "|---:|---:|---:|---:|---:|---:|---|"]
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
     out.append(f"| {a[1] / 1e3:.3f} | {100 * a[1] / tot:.1f}% | {a[0]} | {a[1] / a[0]:.1f} | {a[2] / 1e6:.1f} | {a[3] / 1e6:.1f} | `{k}` |")
-open(os.path.join(ROOT, "profiles", f"r01_launches_step_{tag}.md"), "w").write("\n".join(out) + "\n")
+open(os.path.join(ROOT, "profiles", f"r02_launches_step_{tag}.md"), "w").write("\n".join(out) + "\n")
 traffic = {}
 for k, a in agg.items():
     per_launch = (a[2] + a[3]) / a[0]

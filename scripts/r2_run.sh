@@ -14,6 +14,11 @@ for leg in "$@"; do
     bench) timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.log 2>&1; echo "bench rc=$?" >> $S ;;
     breakdown) timeout 600 python scripts/breakdown.py > gpurun_out/breakdown_$TAG.log 2>&1; echo "breakdown rc=$?" >> $S ;;
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --ncu --steps 1 > gpurun_out/ncu_list_$TAG.log 2>&1; echo "ncu list rc=$?" >> $S ;;
+    ncu_layer) # full capture (source counters) of conv_tc on one layer: NCU_LAYER=name NCU_SKIP=n
+           timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s ${NCU_SKIP:-6} -c 1 -f -o gpurun_out/ncu_${NCU_LAYER:-gen_128_128_k11}_$TAG python scripts/layer_bench.py --only ${NCU_LAYER:-gen_128_128_k11} --iters 2 > gpurun_out/ncu_layer_$TAG.log 2>&1; echo "ncu_layer rc=$?" >> $S ;;
+    graderr) timeout 300 python scripts/grad_err_report.py > gpurun_out/graderr_$TAG.log 2>&1; echo "graderr rc=$?" >> $S ;;
+    torchgpu) timeout 600 python bench.py --impl torch_gpu --steps 5 --warmup 3 > gpurun_out/torchgpu_$TAG.log 2>&1; echo "torchgpu rc=$?" >> $S ;;
+    rbtest) timeout 300 python scripts/rb_test.py > gpurun_out/rbtest_$TAG.log 2>&1; echo "rbtest rc=$?" >> $S; tail -3 gpurun_out/rbtest_$TAG.log >> $S ;;
     *) echo "unknown leg $leg" >> $S ;;
   esac
 done

@@ -63,3 +63,40 @@ for name, (kw, B, T, period, resid) in LAYERS.items():
             print(f"  epilogue warp 0, {ttl}, per 32-column chunk (us): start / TMEM loaded (+fuse2 add) / transposed / stored")
             for n in chunks:
                 print(f"    chunk {n:2d}: " + " ".join(rel(int(t[role, n, e])) for e in range(4)))
+
+
+# ---- epilogue ablation (kt_debug_set_flags): bit 0 no residual loads, 1 no stores, 2 no transposition, 3 no TMEM loads
+print("=== epilogue ablation: us/launch and CTA0 epilogue window of tile 0 (accumulator full -> tile stored)")
+for name in ("gen_128_128_k11", "gen_32_32_k7", "gen_64_64_k7"):
+    kw, B, T, period, resid = LAYERS[name]
+    spec = ops.ConvSpec(**kw)
+    spec.act_in, spec.act_in_slope = KT_ACT_LRELU, 0.1
+    g = torch.Generator().manual_seed(1)
+    v = torch.nn.Parameter((torch.randn((spec.c_out, spec.c_in, spec.kernel), generator=g) * 0.05).cuda(), requires_grad=False)
+    bias = torch.zeros(spec.c_out, device="cuda")
+    x = torch.randn((B, T, spec.c_in), generator=g).cuda()
+    cache = ops.PreparedWeight()
+    with torch.no_grad():
+        y = ops.conv(x, spec, cache, v, None, bias)
+        r = torch.randn_like(y)
+        for flags in (0, 1, 2, 3, 4, 8, 12, 15):
+            lib.kt_debug_set_flags(flags)
+            for _ in range(2):
+                y = ops.conv(x, spec, cache, v, None, bias, r)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                y = ops.conv(x, spec, cache, v, None, bias, r)
+            e1.record(); torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 100
+            tr = torch.zeros(6 * 16 * 4, dtype=torch.int64, device="cuda")
+            lib.kt_debug_set_trace(tr.data_ptr())
+            y = ops.conv(x, spec, cache, v, None, bias, r)
+            torch.cuda.synchronize()
+            lib.kt_debug_set_trace(None)
+            t = tr.cpu().view(6, 16, 4)
+            ep = [(int(t[3, ti, 3]) - int(t[3, ti, 1])) / 1.9e3 for ti in range(2)]
+            mm = [(int(t[2, ti, 3]) - int(t[2, ti, 2])) / 1.9e3 for ti in range(2)]
+            print(f"  {name:18s} flags {flags:2d}: {us:6.1f} us/launch | epilogue tile0 {ep[0]:5.1f} us tile1 {ep[1]:5.1f} us | MMA phase tile0 {mm[0]:5.1f} tile1 {mm[1]:5.1f}")
+        lib.kt_debug_set_flags(0)

@@ -3,6 +3,7 @@
 unmodified reference.  Tolerances (north_star): waveform RMS <= 1e-3, mel-L1 <= 1e-4; we hold the
 exact-fp32 (FFMA) kernels to ~1e-5 relative and the tcgen05 bf16x3 kernels to 1e-4 relative."""
 import math
+import os
 import zlib
 
 import pytest
@@ -151,20 +152,22 @@ def test_conv_layer_tcgen05_vs_oracle(name):
     assert _run_case(name, force_ffma=False), "expected the tcgen05 path to be taken"
 
 
-def _check_param_grads(m, refg, exact):
+def _check_param_grads(m, refg, exact, tol=(5e-4, 1e-3, 1e-2)):
     """Parameter gradients vs the reference's.  Exact-fp32 kernels: every tensor <= 1e-4 relative.  bf16x3
     tensor-core kernels: a weight gradient is a sum over (batch x time) of products carried to ~2^-17, so
     gradients that are small residuals of large cancelling sums lose relative accuracy; the typical tensor
-    must still agree to 5e-4, the whole gradient vector to 1e-3, the worst single (thin) tensor to 3e-2."""
+    must still agree to 5e-4, the whole gradient vector to 1e-3, the worst single (thin) tensor to 1e-2 (round 2: measured
+    worst 5.4e-3 over the four module fixtures, scripts/grad_err_report.py)."""
     errs = sorted((rel_l2(p.grad.cpu(), refg[k]), k) for k, p in m.named_parameters())
     if exact:
         assert errs[-1][0] < 1e-4, errs[-1]
         return
     num = sum(float(((p.grad.cpu() - refg[k]).double() ** 2).sum()) for k, p in m.named_parameters())
     den = sum(float((refg[k].double() ** 2).sum()) for k, p in m.named_parameters())
-    assert errs[len(errs) // 2][0] < 5e-4, ("median", errs[len(errs) // 2])
-    assert (num / den) ** 0.5 < 1e-3, ("global", (num / den) ** 0.5)
-    assert errs[-1][0] < 3e-2, ("worst", errs[-1], errs[-5:])
+    print("param-grad rel err: median %.2e global %.2e worst %s" % (errs[len(errs) // 2][0], (num / den) ** 0.5, errs[-3:]))
+    assert errs[len(errs) // 2][0] < tol[0], ("median", errs[len(errs) // 2])
+    assert (num / den) ** 0.5 < tol[1], ("global", (num / den) ** 0.5)
+    assert errs[-1][0] < tol[2], ("worst", errs[-1], errs[-5:])
 
 
 def _load(module, sd):
@@ -395,3 +398,107 @@ def test_full_size_properties():
     mel = K.MelSpectrogram().to(DEV)
     out = mel(torch.zeros(B, 1, T, device=DEV))
     assert out.shape == (B, 80, 33) and float(out.max()) == -4.0
+
+
+@pytest.mark.parametrize("force_ffma", [False, True])
+def test_full_size_c2_train_step_matches_oracle(force_ffma):
+    """BASELINE configs[1] at FULL size (B = 16 x 8192 samples, class-default generator, yaml MSD + MPD -- the very
+    workload bench.py times): one GanStep (eager launches, default bf16x3 tensor-core path) against
+    oracle.OracleGAN.train_step on the host, same reference-constructed weights and the same synthetic batch: the
+    seven logged losses, every parameter-gradient tensor of both phases, and the parameters after the three Adam
+    steps ('configs never compared with the oracle on GPU')."""
+    import bench
+    from oracle import hifigan as O
+    torch.manual_seed(1234)
+    model, opt, sched = K.hifigan_model_builder(bench.CONFIG, torch.device(DEV))
+    crit = K.criterion_builder(bench.CONFIG, torch.device(DEV))
+    G, D = model["generator"], model["discriminator"]
+    before = {"g": {k: v.detach().cpu().clone() for k, v in G.state_dict().items()},
+              **{n: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()} for n, m in D.items()}}
+    gan = O.OracleGAN(before["g"], {n: before[n] for n in D}, bench.G_PARAMS,
+                      {"MultiScaleDiscriminator": bench.MSD_PARAMS, "MultiPeriodDiscriminator": bench.MPD_PARAMS}, bench.LOSS)
+    y, x = bench.synth_batch(bench.B_PER_GPU, 1234)
+    step = K.GanStep(model, opt, sched, crit, bench.CONFIG)
+    ops.set_force_ffma(force_ffma)      # True: the exact-fp32 kernels -- separates split-precision effects from logic errors
+    try:
+        log = K.train.losses_to_float(step.step((y.to(DEV), x.to(DEV))))
+        torch.cuda.synchronize()
+    finally:
+        ops.set_force_ffma(False)
+    torch.set_num_threads(min(os.cpu_count() or 1, 32))
+    ref = gan.train_step(y, x)
+    for k in ("mel_loss", "adversarial_loss", "feature_matching_loss", "generator_loss", "real_loss", "fake_loss", "discriminator_loss"):
+        assert abs(log[k] - ref[k]) <= 2e-4 * max(1.0, abs(ref[k])), (k, log[k], ref[k])
+    for tag, m, od in (("g", G, gan.g), ("msd", D["MultiScaleDiscriminator"], gan.d["MultiScaleDiscriminator"]),
+                       ("mpd", D["MultiPeriodDiscriminator"], gan.d["MultiPeriodDiscriminator"])):
+        refg = {k: od[k].grad for k, _ in m.named_parameters()}
+        # full size: 131 072 output rows per weight gradient and ~100 LeakyReLUs upstream of every tensor -- the ~1e-5
+        # forward difference flips the derivative mask of the pre-activations nearest zero (a discontinuous function of
+        # the forward), which dominates the per-tensor figure (measured: -s output of this test)
+        _check_param_grads(m, refg, exact=False, tol=(1e-4, 1e-4, 2e-3) if force_ffma else (5e-3, 5e-3, 1e-1))
+        sd = m.state_dict()
+        num = den = 0.0
+        for k, v in od.items():
+            if not v.is_floating_point():
+                continue
+            b = before["g" if tag == "g" else {"msd": "MultiScaleDiscriminator", "mpd": "MultiPeriodDiscriminator"}[tag]][k]
+            num += float(((sd[k].cpu() - v.detach()).double() ** 2).sum())
+            den += float(((b - v.detach()).double() ** 2).sum())
+        assert num <= 2e-2 * den, (tag, num, den)
+
+
+RB_CASES = {
+    # name: (channels, kernel, dilation, causal, B, T)
+    "rb64_k3_d1_causal": (64, 3, 1, True, 2, 300),
+    "rb64_k7_d3_causal": (64, 7, 3, True, 2, 515),
+    "rb64_k11_d5_noncausal": (64, 11, 5, False, 2, 999),
+    "rb32_k3_d1_noncausal": (32, 3, 1, False, 2, 300),
+    "rb32_k7_d5_causal": (32, 7, 5, True, 3, 1000),
+    "rb32_k11_d5_causal": (32, 11, 5, True, 2, 777),
+    "rb32_k11_d3_short": (32, 11, 3, True, 2, 64),          # T shorter than one tile / than the receptive field
+}
+
+
+@pytest.mark.parametrize("name", sorted(RB_CASES))
+def test_fused_resblock_unit_vs_oracle(name):
+    """kt_resblock_fwd / kt_resblock_bwd (SURVEY 8 row G4 / VERDICT row K1: one (convs1[i], convs2[i]) pair of
+    layers.py:213-220 in ONE launch) against the layer oracle: y, and every gradient (x, both weights_v / weight_g, both
+    biases), with weight norm on, ragged tile counts, causal and centred padding."""
+    C, k, d, causal, B, T = RB_CASES[name]
+    p1 = (k - 1) * d if causal else (k - 1) * d // 2
+    p2 = (k - 1) if causal else (k - 1) // 2
+    s1 = ops.ConvSpec(c_in=C, c_out=C, kernel=k, dilation=d, pad_left=p1, pad_right=(k - 1) * d - p1, act_in=KT_ACT_LRELU, act_in_slope=0.1)
+    s2 = ops.ConvSpec(c_in=C, c_out=C, kernel=k, dilation=1, pad_left=p2, pad_right=(k - 1) - p2, act_in=KT_ACT_LRELU, act_in_slope=0.1)
+    gen = torch.Generator().manual_seed(zlib.crc32(name.encode()))
+    prm = []
+    for _ in range(2):
+        v = torch.randn(C, C, k, generator=gen) / math.sqrt(C * k)
+        g = v.norm(2, dim=(1, 2), keepdim=True) * (1 + 0.2 * torch.randn(C, 1, 1, generator=gen))
+        b = 0.1 * torch.randn(C, generator=gen)
+        prm += [v, g, b]
+    x = torch.randn(B, C, T, generator=gen)
+    r = torch.randn(B, C, T, generator=gen)
+    # ---- oracle (CPU, channels-first)
+    ref_in = [t.clone().requires_grad_(True) for t in [x] + prm]
+    xo, v1, g1, b1, v2, g2, b2 = ref_in
+    w1 = g1 * v1 / v1.norm(2, dim=(1, 2), keepdim=True)
+    w2 = g2 * v2 / v2.norm(2, dim=(1, 2), keepdim=True)
+    ho = convref.conv_layer(xo, w1, b1, dilation=d, pad_left=p1, pad_right=(k - 1) * d - p1, act_in=0.1)
+    yo = convref.conv_layer(ho, w2, b2, resid=xo, dilation=1, pad_left=p2, pad_right=(k - 1) - p2, act_in=0.1)
+    (yo * r).sum().backward()
+    # ---- product: the fused unit on channels-last rows
+    dev_in = [torch.nn.Parameter(t.clone().to(DEV)) for t in prm]
+    xg = x.permute(0, 2, 1).contiguous().to(DEV).requires_grad_(True)
+    rd = ops.resblock_desc(s1, s2, B, T)
+    assert rd is not None, "the fused kernel must support this shape"
+    n0 = ops.tc_launch_count()
+    y = ops.resblock(xg, s1, ops.PreparedWeight(), dev_in[0], dev_in[1], dev_in[2], s2, ops.PreparedWeight(), dev_in[3], dev_in[4],
+                     dev_in[5], rd)
+    assert ops.tc_launch_count() == n0 + 1                                  # ONE launch for the pair
+    assert rel_l2(y.detach().cpu().permute(0, 2, 1), yo.detach()) < 1e-4
+    (y * r.permute(0, 2, 1).contiguous().to(DEV)).sum().backward()
+    K.hifigan.join_side_streams(torch.device(DEV))
+    torch.cuda.synchronize()
+    assert rel_l2(xg.grad.cpu().permute(0, 2, 1), xo.grad) < 2e-4
+    for got, want, nm in zip(dev_in, ref_in[1:], ("v1", "g1", "b1", "v2", "g2", "b2")):
+        assert rel_l2(got.grad.cpu(), want.grad) < 1e-3, (nm, rel_l2(got.grad.cpu(), want.grad))
