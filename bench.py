@@ -181,6 +181,83 @@ def torch_gpu_main(args, rank, local_rank):
                       "losses": {"generator": float(gl), "discriminator": float(dl)}}), flush=True)
 
 
+def side_workload_main(args, rank, local_rank):
+    """BASELINE configs[0] / configs[3] on one GPU: informational lines (the driver's headline is
+    the default workload).  C1: class-default Generator, eval, weight norm removed, mel (1, 80, 32) -> 8192 samples,
+    audio samples / s.  C4: SAM-BERT (sambert_24k.yaml sizes) train step, B = 32, 256 symbols, 768 mel frames, mel frames / s;
+    roofline = algorithmic forward + backward FLOPs (3 x 136.4 GMAC x 2) against the bf16x3 tensor peak."""
+    if rank != 0:
+        return
+    import kantts_b200 as K
+    from kantts_b200 import ops
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    torch.manual_seed(1234)
+    W = max(3, args.warmup)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    bf16 = json.load(open(peaks_path)).get("bf16_tflops_sustained", 1437.7) if os.path.exists(peaks_path) else 1400.0
+    if args.workload == "c1":
+        g = K.Generator(**G_PARAMS).to(dev).eval()
+        g.remove_weight_norm()
+        x = torch.randn(1, 80, 32, generator=torch.Generator().manual_seed(1234)).to(dev)
+        with torch.no_grad():
+            for _ in range(W):
+                y = g(x)
+            torch.cuda.synchronize()
+            n0 = ops.launch_count()
+            e0.record()
+            for _ in range(args.steps):
+                y = g(x)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        flops = 2 * 10.88e9
+        line = {"metric": "hifigan_generator_forward_audio_samples_per_sec", "value": 8192 / (ms * 1e-3), "unit": "samples/s",
+                "config": {"workload": "HiFi-GAN v1 generator forward, batch=1, 80-mel x 32 frames (BASELINE configs[0])",
+                           "note": "eval, remove_weight_norm, eager launches (latency-bound: one utterance, ~100 launches)"},
+                "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": bf16 / 3, "unit": "TFLOP/s",
+                             "frac": flops / (ms * 1e-3) / 1e12 / (bf16 / 3), "traffic": None},
+                "gpu_launches": ops.launch_count() - n0}
+    else:
+        from kantts_b200 import sambert
+        cfg = K.sambert_24k_config()
+        model = sambert.KanTtsSAMBERT(cfg).to(dev).train()
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.98), eps=1e-9)
+        sch = K.train.NoamLR(opt, warmup_steps=4000)
+        step = K.SambertStep(model, opt, sch, {"MelReconLoss": sambert.MelReconLoss(), "ProsodyReconLoss": sambert.ProsodyReconLoss()})
+        gen = torch.Generator().manual_seed(1234)
+        B, L, dur = 32, 256, 3
+        ling = torch.stack([torch.randint(0, cfg[k], (B, L), generator=gen) for k in ("sy", "tone", "syllable_flag", "word_segment")], -1)
+        batch = dict(input_lings=ling, input_emotions=torch.randint(0, cfg["emotion"], (B, L), generator=gen),
+                     input_speakers=torch.randint(0, cfg["speaker"], (B, L), generator=gen),
+                     valid_input_lengths=torch.full((B,), L - 1, dtype=torch.long),
+                     valid_output_lengths=torch.full((B,), L * dur, dtype=torch.long),
+                     mel_targets=torch.randn(B, L * dur, cfg["num_mels"], generator=gen), durations=torch.full((B, L), dur, dtype=torch.long),
+                     pitch_contours=torch.randn(B, L, generator=gen), energy_contours=torch.randn(B, L, generator=gen))
+        batch = {k: v.to(dev) for k, v in batch.items()}
+        for _ in range(W):
+            out = step.step(batch)
+        torch.cuda.synchronize()
+        n0 = ops.launch_count()
+        e0.record()
+        for _ in range(args.steps):
+            out = step.step(batch)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        flops = 3 * 2 * 136.4e9
+        line = {"metric": "sambert_train_step_mel_frames_per_sec", "value": B * L * dur / (ms * 1e-3), "unit": "mel frames/s",
+                "config": {"workload": "SAM-BERT acoustic model fwd/bwd + Adam, batch=32, seq_len=256, 768 x 80-mel targets (BASELINE configs[3])",
+                           "note": "train() mode (dropout on), eager launches, the four LSTMs on cuDNN (SURVEY 2c)"},
+                "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": bf16 / 3, "unit": "TFLOP/s",
+                             "frac": flops / (ms * 1e-3) / 1e12 / (bf16 / 3), "traffic": None},
+                "gpu_launches": (ops.launch_count() - n0) // args.steps, "loss": float(out["TotalLoss"])}
+    line.update({"n_gpus": 1, "steps": args.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "dtype": "f32",
+                 "data": "synthetic", "vs_baseline": None})
+    print(json.dumps(line), flush=True)
+
+
 # ---------------------------------------------------------------------------------------------------
 # clocks
 # ---------------------------------------------------------------------------------------------------
@@ -231,6 +308,9 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference", "torch_gpu"],
                     help="native: this repo's CUDA path; reference: the reference's CPU path (oracle port) on the host cores; "
                          "torch_gpu: stock PyTorch (cuDNN fp32, TF32 off) on the same GPU -- informational baseline")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c1", "c4"],
+                    help="c2 (default, the headline: BASELINE configs[1]); c1: generator forward B = 1 (configs[0]); c4: SAM-BERT "
+                         "train step B = 32 x 256 symbols x 768 frames (configs[3]) -- informational lines with their own metric")
     ap.add_argument("--cpu-sample-batch", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -249,6 +329,8 @@ def main():
         return reference_main(args, rank)
     if args.impl == "torch_gpu":
         return torch_gpu_main(args, rank, local_rank)
+    if args.workload != "c2":
+        return side_workload_main(args, rank, local_rank)
     if world != args.gpus:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torchrun (one rank per GPU)")
     if not torch.cuda.is_available():

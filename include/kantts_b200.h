@@ -259,6 +259,18 @@ int kt_rows_gather_fwd(const float* in, const int32_t* idx, float* out, int32_t 
 int kt_rows_gather_bwd(const float* dout, const int32_t* idx, const int32_t* start, const int32_t* count, float* din,
                        int32_t batch, int32_t t_out, int32_t t_in, int32_t c, void* stream);
 
+/* Autoregressive duration predictor, free-running inference (VarRnnARPredictor.infer, kantts/models/sambert/adaptors.py:67-83):
+ * the whole per-symbol recurrence  x -> Prenet(1 -> p1 -> p2, ReLU) -> cat(cond) -> 2-layer LSTM(hidden) -> Linear(hidden, 1) ->
+ * ReLU -> next x  in ONE launch (one CTA per batch item) instead of ~10 library launches per symbol from Python.
+ *   g0c   [batch][length][4*hidden] = cond . weight_ih_l0[:, p2:]^T + bias_ih_l0 + bias_hh_l0   (precomputed, one GEMM)
+ *   w1 [p1] = prenet Linear(1,p1).weight[:,0], b1 [p1]; w2t [p1][p2] = Linear(p1,p2).weight^T, b2 [p2]
+ *   wih0t [p2][4h] = weight_ih_l0[:, :p2]^T, whh0t [h][4h] = weight_hh_l0^T; wih1t / whh1t [h][4h]; bias1 [4h] = bias_ih_l1 + bias_hh_l1
+ *   fcw [h], fcb: the output Linear; out [batch][length] (before the padding mask). */
+int kt_ar_duration_infer(const float* g0c, const float* w1, const float* b1, const float* w2t, const float* b2,
+                         const float* wih0t, const float* whh0t, const float* wih1t, const float* whh1t,
+                         const float* bias1, const float* fcw, float fcb, float* out, int32_t batch, int32_t length,
+                         int32_t hidden, int32_t p1, int32_t p2, void* stream);
+
 /* ---- fused ResidualBlock unit (kantts/models/hifigan/layers.py:213-220, one (convs1[i], convs2[i]) pair) ----------
  *   h = conv(leaky_relu(x); w1, dilation d, pad_left1) + b1
  *   y = conv(leaky_relu(h); w2, dilation 1, pad_left2) + b2 + x

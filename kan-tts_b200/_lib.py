@@ -74,6 +74,7 @@ PROTOTYPES = {
     "kt_conv1d_bwd_data_tc": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P],
     "kt_conv1d_bwd_weight_tc_workspace": [ctypes.POINTER(KtConv1dDesc)],
     "kt_conv1d_bwd_weight_tc": [ctypes.POINTER(KtConv1dDesc), _P, _P, _P, _P, _P, _P, _L, _P],
+    "kt_ar_duration_infer": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _I, _I, _I, _I, _I, _P],
     "kt_resblock_plan": [ctypes.POINTER(KtResblockDesc)],
     "kt_resblock_image_bytes": [ctypes.POINTER(KtResblockDesc)],
     "kt_resblock_pack": [ctypes.POINTER(KtResblockDesc), _P, _P, _P],

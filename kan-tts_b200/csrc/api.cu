@@ -28,6 +28,8 @@ long long tc_image_bytes(const KtConv1dDesc*, int);
 int tc_pack_layer(const KtConv1dDesc*, int, const float*, void*, cudaStream_t);
 int conv1d_fwd_tc(const KtConv1dDesc*, const float*, const void*, const float*, const float*, float*, cudaStream_t);
 int conv1d_bwd_data_tc(const KtConv1dDesc*, const float*, const float*, const void*, const float*, float*, cudaStream_t);
+int ar_duration_infer(const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*,
+                      const float*, const float*, const float*, float, float*, int, int, int, int, int, cudaStream_t);
 int resblock_plan(const KtResblockDesc*);
 long long resblock_image_bytes(const KtResblockDesc*);
 int resblock_pack(const KtResblockDesc*, const float*, void*, cudaStream_t);
@@ -172,6 +174,12 @@ int kt_conv1d_bwd_data_tc(const KtConv1dDesc* d, const float* dy, const float* y
   return kt::conv1d_bwd_data_tc(d, dy, y, wimg, x, dx, ST(stream));
 }
 
+int kt_ar_duration_infer(const float* g0c, const float* w1, const float* b1, const float* w2t, const float* b2, const float* wih0t,
+                         const float* whh0t, const float* wih1t, const float* whh1t, const float* bias1, const float* fcw, float fcb,
+                         float* out, int32_t batch, int32_t length, int32_t hidden, int32_t p1, int32_t p2, void* stream) {
+  return kt::ar_duration_infer(g0c, w1, b1, w2t, b2, wih0t, whh0t, wih1t, whh1t, bias1, fcw, fcb, out, batch, length, hidden, p1, p2,
+                               ST(stream));
+}
 int kt_resblock_plan(const KtResblockDesc* d) { return d ? kt::resblock_plan(d) : 0; }
 int64_t kt_resblock_image_bytes(const KtResblockDesc* d) { return d ? kt::resblock_image_bytes(d) : 0; }
 int kt_resblock_pack(const KtResblockDesc* d, const float* w_fwd, void* img, void* stream) {

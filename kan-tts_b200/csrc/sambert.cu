@@ -897,4 +897,109 @@ int rows_gather_bwd(const float* dout, const int* idx, const int* start, const i
   return KT_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Autoregressive duration predictor, whole recurrence in ONE launch (VarRnnARPredictor.infer,
+// kantts/models/sambert/adaptors.py:67-83: per symbol  x -> Prenet(1 -> P1 -> P2, ReLU) -> cat(cond) -> 2-layer LSTM ->
+// Linear(H -> 1) -> ReLU -> fed back as the next symbol's input).  The reference runs ~10 library launches per symbol
+// from a Python loop (L = 256 symbols: ~2500 launches, pure latency); here one CTA per batch item walks the L steps,
+// 4H threads = one thread per LSTM gate, activations / states in shared memory, the (transposed) weights streamed from
+// L2 with coalesced loads.  The condition's share of the layer-0 input projection does not depend on the recurrence and
+// arrives precomputed: g0c[b][i][4H] = cond[b][i] . W_ih0[:, P2:]^T + b_ih0 + b_hh0 (one GEMM for all symbols).
+// PyTorch gate order (i, f, g, o); exact fp32.
+// ---------------------------------------------------------------------------------------------
+struct ArDurParams {
+  const float* g0c;                 // [B][L][4H]
+  const float *w1, *b1;             // [P1] (Linear(1, P1).weight[:, 0]), [P1]
+  const float *w2t, *b2;            // [P1][P2] = Linear(P1, P2).weight^T, [P2]
+  const float *wih0t, *whh0t;       // [P2][4H] (prenet columns of weight_ih_l0, transposed), [H][4H]
+  const float *wih1t, *whh1t, *bias1;   // [H][4H], [H][4H], [4H] = b_ih1 + b_hh1
+  const float* fcw;                 // [H]
+  float fcb;
+  float* out;                       // [B][L]
+  int L, H, P1, P2;
+};
+
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.f / (1.f + expf(-v)); }
+
+__global__ void ar_duration_kernel(const ArDurParams p) {
+  extern __shared__ float sm[];
+  const int H = p.H, G = 4 * H;
+  float* p1 = sm;            // [P1]
+  float* p2 = p1 + p.P1;     // [P2]
+  float* h0 = p2 + p.P2;     // [H]
+  float* c0 = h0 + H;
+  float* h1 = c0 + H;
+  float* c1 = h1 + H;
+  float* gates = c1 + H;     // [4H]
+  float* xs = gates + G;     // [1]
+  const int tid = threadIdx.x, b = blockIdx.x;
+  for (int t = tid; t < 4 * H; t += blockDim.x) h0[t] = 0.f;     // h0, c0, h1, c1 are contiguous
+  if (tid == 0) xs[0] = 0.f;
+  __syncthreads();
+  const float* g0 = p.g0c + (long long)b * p.L * G;
+  for (int i = 0; i < p.L; ++i) {
+    const float x = xs[0];
+    for (int t = tid; t < p.P1; t += blockDim.x) p1[t] = fmaxf(fmaf(__ldg(p.w1 + t), x, __ldg(p.b1 + t)), 0.f);
+    __syncthreads();
+    for (int t = tid; t < p.P2; t += blockDim.x) {
+      float acc = __ldg(p.b2 + t);
+      for (int k = 0; k < p.P1; ++k) acc = fmaf(__ldg(p.w2t + k * p.P2 + t), p1[k], acc);
+      p2[t] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    for (int j = tid; j < G; j += blockDim.x) {
+      float acc = __ldg(g0 + (long long)i * G + j);
+      for (int k = 0; k < p.P2; ++k) acc = fmaf(__ldg(p.wih0t + k * G + j), p2[k], acc);
+      for (int k = 0; k < H; ++k) acc = fmaf(__ldg(p.whh0t + k * G + j), h0[k], acc);
+      gates[j] = acc;
+    }
+    __syncthreads();
+    for (int t = tid; t < H; t += blockDim.x) {
+      const float ig = sigmoid_f(gates[t]), fg = sigmoid_f(gates[H + t]), gg = tanhf(gates[2 * H + t]), og = sigmoid_f(gates[3 * H + t]);
+      const float c = fg * c0[t] + ig * gg;
+      c0[t] = c;
+      h0[t] = og * tanhf(c);
+    }
+    __syncthreads();
+    for (int j = tid; j < G; j += blockDim.x) {
+      float acc = __ldg(p.bias1 + j);
+      for (int k = 0; k < H; ++k) acc = fmaf(__ldg(p.wih1t + k * G + j), h0[k], acc);
+      for (int k = 0; k < H; ++k) acc = fmaf(__ldg(p.whh1t + k * G + j), h1[k], acc);
+      gates[j] = acc;
+    }
+    __syncthreads();
+    for (int t = tid; t < H; t += blockDim.x) {
+      const float ig = sigmoid_f(gates[t]), fg = sigmoid_f(gates[H + t]), gg = tanhf(gates[2 * H + t]), og = sigmoid_f(gates[3 * H + t]);
+      const float c = fg * c1[t] + ig * gg;
+      c1[t] = c;
+      h1[t] = og * tanhf(c);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      float acc = 0.f;
+      for (int k = tid; k < H; k += 32) acc = fmaf(__ldg(p.fcw + k), h1[k], acc);
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (tid == 0) {
+        const float y = fmaxf(acc + p.fcb, 0.f);
+        xs[0] = y;
+        p.out[(long long)b * p.L + i] = y;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+int ar_duration_infer(const float* g0c, const float* w1, const float* b1, const float* w2t, const float* b2, const float* wih0t,
+                      const float* whh0t, const float* wih1t, const float* whh1t, const float* bias1, const float* fcw, float fcb,
+                      float* out, int B, int L, int H, int P1, int P2, cudaStream_t st) {
+  KT_REQUIRE(g0c && w1 && b1 && w2t && b2 && wih0t && whh0t && wih1t && whh1t && bias1 && fcw && out, "ar_duration_infer: null pointer");
+  KT_REQUIRE(B >= 1 && L >= 1 && H >= 1 && H <= 256 && P1 >= 1 && P2 >= 1 && P1 <= 1024 && P2 <= 1024, "ar_duration_infer: bad sizes");
+  ArDurParams p{g0c, w1, b1, w2t, b2, wih0t, whh0t, wih1t, whh1t, bias1, fcw, fcb, out, L, H, P1, P2};
+  const int threads = std::min(1024, std::max(32, ((4 * H + 31) / 32) * 32));
+  const size_t smem = (size_t)(P1 + P2 + 8 * H + 1) * sizeof(float);
+  ar_duration_kernel<<<B, threads, smem, st>>>(p);
+  KT_CHECK_CUDA(cudaGetLastError());
+  return KT_OK;
+}
+
 }  // namespace kt

@@ -54,6 +54,11 @@ struct WgTcParams {
   int unit_ntaps[kMaxTaps];    // 1 or 2
   int tap_j[kMaxTaps];
   int tap_q[kMaxTaps];
+  // bias gradient as one more accumulator unit of unit group `bias_grp` (-1: none): D[m][n] += sum_rows 1 * B[row][n] with an
+  // all-ones A operand -- every accumulator row is the column sum of the (masked) output gradient over this CTA's rows, row 0
+  // goes to the split's slice of the workspace at `bias_off` and wgrad_reduce sums the splits like any other element
+  int bias_grp;
+  long long bias_off, split_stride;
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
@@ -71,6 +76,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   uint64_t* tmem_full = bars + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
   uint32_t* s_unit = tmem_slot + 2;     // [kWgMaxUnits] per unit of this CTA: A-side row shift (16-byte units) | LBO field
+  uint8_t* ones_img = reinterpret_cast<uint8_t*>(bars) + 128;   // (kWgTK + 8) rows x 128 B of bf16 1.0 (only when bias_grp >= 0)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cb_tile = blockIdx.x % p.n_cb_tiles;
@@ -82,6 +88,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   const int qlo = p.grp_qlo[grp];
   const int split = blockIdx.z;
 
+  const bool has_bias = p.bias_grp == (int)blockIdx.y && ca_tile == 0;
   const long long units = (long long)p.batch * p.chunks_per_batch;
   const long long c_begin = units * split / p.nsplit;
   const long long c_end = units * (split + 1) / p.nsplit;
@@ -93,6 +100,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     fence_proxy_async();
   }
   if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  if (has_bias) {   // uniform data: invariant under the 128-byte swizzle, any 16-byte-aligned start address works
+    for (int i = tid; i < (kWgTK + 8) * 128 / 16; i += kWgThreads) reinterpret_cast<uint4*>(ones_img)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async();
+  }
   if (tid >= 160 && tid < 160 + nu) {
     const int u = tid - 160;
     const int n_a = p.unit_tap0[u0 + u];
@@ -164,10 +175,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         if (p.gt > 1) {   // block diagonal: row of conv group gl keeps only that group's cb_g0 columns
           const int gl = ca_idx / p.ca_g0, ci_l = ca_idx - gl * p.ca_g0;
           c_lo = gl * p.cb_g0; c_hi = c_lo + p.cb_g0;
-          obase = (((long long)split * p.taps_total + p.tap_j[tap_n]) * p.ca_g0 + ci_l) * p.cb +
+          obase = (long long)split * p.split_stride + (((long long)p.tap_j[tap_n]) * p.ca_g0 + ci_l) * p.cb +
                   ((long long)cgrp * p.gt + gl) * p.cb_g0 - c_lo;
         } else {
-          obase = (((long long)split * p.taps_total + p.tap_j[tap_n]) * p.ca_g + ca_idx) * p.cb + (long long)cgrp * p.cb_g + col0;
+          obase = (long long)split * p.split_stride + (((long long)p.tap_j[tap_n]) * p.ca_g + ca_idx) * p.cb + (long long)cgrp * p.cb_g + col0;
         }
       }
       const bool vec = ((p.cb | p.cb_g0) & 3) == 0;
@@ -191,6 +202,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         }
       }
     }
+    if (has_bias && warp == 0) {   // accumulator unit `nu`: every row = column sums; row 0 (lane 0) stores them
+      const int col0 = cb_tile * p.NT;
+      const int ncol = min(p.NT, p.cb_g - col0);
+      float* dst = p.ws + (long long)split * p.split_stride + p.bias_off + (long long)cgrp * p.cb_g + col0;
+      for (int n0 = 0; n0 < p.NT; n0 += 32) {
+        uint32_t rr[32];
+        tmem_ld32(tmem_acc + (uint32_t)(nu * p.NT + n0), rr);
+        tmem_ld_wait();
+        if (lane == 0) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (n0 + e < ncol) dst[n0 + e] = __uint_as_float(rr[e]);
+        }
+      }
+    }
     }
     tc_fence_before();
   } else if (warp == 5) {
@@ -203,6 +229,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       const uint32_t img_a16 = (uint32_t)img_a >> 4, img_b16 = (uint32_t)img_b >> 4;
       const uint32_t st16[2] = {smem_u32(stage0) >> 4, smem_u32(stage0 + stage_bytes) >> 4};
       const uint32_t boff16 = (uint32_t)(p.a_groups * 2 * img_a) >> 4;
+      const uint32_t ones16 = (smem_u32(ones_img) >> 4) | ((128u >> 4) << 16);   // second 64-channel half of M: one row further (all ones)
       int it = 0;
       for (long long c = c_begin; c < c_end; ++c, ++it) {
         const int s = it & 1;
@@ -223,6 +250,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             umma_bf16_lo(d, a_hi + ko, b_hi + ko, idesc, 1u);
           }
         }
+        if (has_bias) {   // ones^T x (b_hi + b_lo): two MMAs per K slice into accumulator unit `nu`
+          const uint32_t d = tmem_acc + (uint32_t)(nu * p.NT);
+#pragma unroll
+          for (int ks = 0; ks < kWgTK / 16; ++ks) {
+            const uint32_t ko = (uint32_t)ks * 128u;
+            umma_bf16_lo(d, ones16 + ko, b_hi + ko, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16_lo(d, ones16 + ko, b_hi + img_b16 + ko, idesc, 1u);
+          }
+        }
         umma_commit(&empty[s]);
       }
       umma_commit(tmem_full);
@@ -237,20 +273,30 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   }
 }
 
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n, int nsplit) {
-  if (n & 3) {  // thin layers: split slices are not 16-byte aligned
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+// sums the split-K partials: ws = [nsplit][stride] with stride >= n + nb; elements [0, n) -> dw, [bias_off, bias_off + nb) -> dbias
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n, int nsplit, long long stride,
+                                    float* __restrict__ dbias, long long bias_off, int nb) {
+  const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
+  if (dbias) {
+    for (long long i = gtid; i < nb; i += gsz) {
+      float acc = 0.f;
+      for (int s = 0; s < nsplit; ++s) acc += ws[(long long)s * stride + bias_off + i];
+      dbias[i] = acc;
+    }
+  }
+  if ((n & 3) || (stride & 3)) {  // thin layers: split slices are not 16-byte aligned
+    for (long long i = gtid; i < n; i += gsz) {
       float acc = ws[i];
-      for (int s = 1; s < nsplit; ++s) acc += ws[(long long)s * n + i];
+      for (int s = 1; s < nsplit; ++s) acc += ws[(long long)s * stride + i];
       dw[i] = acc;
     }
     return;
   }
   const long long n4 = n / 4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+  for (long long i = gtid; i < n4; i += gsz) {
     float4 acc = __ldg(reinterpret_cast<const float4*>(ws) + i);
     for (int s = 1; s < nsplit; ++s) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(ws + (long long)s * n) + i);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(ws + (long long)s * stride) + i);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     reinterpret_cast<float4*>(dw)[i] = acc;
@@ -336,6 +382,15 @@ static WgPlan make_plan(const KtConv1dDesc* d) {
   const size_t stage = 2 * ((size_t)p.a_groups * p.rows_a * 128 + (size_t)p.b_groups * kWgTK * 128);
   pl.smem = 1024 + 2 * stage + 128;
   if (pl.smem > (size_t)kMaxDynSmem) return pl;   // (a smaller U would shrink the halo; not needed for the shipped shapes)
+  // bias gradient: one spare accumulator unit in some unit group (the LAST group with fewer than U units) + the ones image.
+  // Only for a plain conv (the bias belongs to the B side = output gradient); transposed convs keep the column-sum kernel.
+  p.bias_grp = -1;
+  if (!tr) {
+    for (int g = p.ngroups - 1; g >= 0; --g)
+      if (p.grp_first_unit[g + 1] - p.grp_first_unit[g] < U) { p.bias_grp = g; break; }
+    if (p.bias_grp >= 0 && pl.smem + (kWgTK + 8) * 128 > (size_t)kMaxDynSmem) p.bias_grp = -1;
+    if (p.bias_grp >= 0) pl.smem += (kWgTK + 8) * 128;
+  }
   p.tmem_cols = 32;
   while (p.tmem_cols < U * p.NT) p.tmem_cols <<= 1;
   if (p.tmem_cols > 512) return pl;
@@ -353,7 +408,10 @@ static WgPlan make_plan(const KtConv1dDesc* d) {
     if (cost < best - 1e-9) { best = cost; nsplit = ns; }
   }
   p.nsplit = (int)nsplit;
-  pl.ws_floats = nsplit * (long long)p.taps_total * p.ca_g0 * cb;
+  const long long n_main = (long long)p.taps_total * p.ca_g0 * cb;
+  p.bias_off = n_main;
+  p.split_stride = n_main + (p.bias_grp >= 0 ? ((cb + 3) & ~3) : 0);
+  pl.ws_floats = nsplit * p.split_stride;
   pl.ok = true;
   return pl;
 }
@@ -394,9 +452,10 @@ int conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy,
   KT_CHECK_CUDA(cudaGetLastError());
   const long long n = (long long)p.taps_total * p.ca_g0 * p.cb;
   const int blocks = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, 148LL * 8));
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dw, n, p.nsplit);
+  const bool fused_bias = dbias != nullptr && p.bias_grp >= 0;
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dw, n, p.nsplit, p.split_stride, fused_bias ? dbias : nullptr, p.bias_off, d->c_out);
   KT_CHECK_CUDA(cudaGetLastError());
-  if (dbias) {
+  if (dbias && !fused_bias) {
     const long long rows = (long long)d->batch * d->nsub * d->t_out;
     int rc = colsum_bias(sdy, rows, d->c_out, dbias, st);
     if (rc) return rc;

@@ -30,6 +30,7 @@ from ._lib import KT_ACT_LRELU, KT_ACT_NONE, KT_ACT_TANH, KT_PATH_AUTO
 
 
 _PARALLEL_STREAMS = os.environ.get("KANTTS_B200_STREAMS", "1") != "0"
+_SPECTRAL_ON_MAIN = os.environ.get("KANTTS_B200_SPECTRAL_ON_MAIN", "1") != "0"
 _STREAMS = {}
 
 
@@ -633,10 +634,25 @@ class DWT1DForward(nn.Module):
 
 
 class _AvgPoolRows(nn.Module):
-    def __init__(self, kernel_size, stride, padding):
+    """nn.AvgPool1d(kernel_size, stride, padding) on the mono waveform (hifigan.py:456-458, count_include_pad=True): a
+    1 -> 1 channel FIR with constant taps 1/k on the C_in = 1 kernels (kt_conv1d_fwd / _bwd_data); no parameters, no
+    buffers (like the reference's pooling module, it adds nothing to the state_dict)."""
+
+    def __init__(self, kernel_size=4, stride=2, padding=2):
         super().__init__()
-        raise NotImplementedError("kantts_b200: AvgPool1d down-sampling is not used by the shipped configs "
-                                  "(downsample_pooling: DWT); not implemented")
+        self.spec = ops.ConvSpec(c_in=1, c_out=1, kernel=int(kernel_size), stride=int(stride), pad_left=int(padding),
+                                 pad_right=int(padding))
+        self._cache = ops.PreparedWeight()
+        self._w = None
+
+    def run(self, rows):
+        """rows: (B, T, 1) -> (B, T2, 1)"""
+        if self._w is None or self._w.device != rows.device:
+            self._w = torch.full((1, 1, self.spec.kernel), 1.0 / self.spec.kernel, device=rows.device)
+        return ops.conv(rows, self.spec, self._cache, self._w)
+
+    def forward(self, y):
+        return self.run(y.transpose(1, 2).contiguous()).transpose(1, 2)
 
 
 class MultiScaleDiscriminator(nn.Module):
@@ -695,8 +711,11 @@ class MultiScaleDiscriminator(nn.Module):
         rows = y.transpose(1, 2).contiguous()                                 # (B, T, 1)
         inputs = [rows]
         for i in range(1, len(self.discriminators)):                          # the pooling chain is cheap and serial
-            cat = ops.DwtFn.apply(rows.reshape(rows.shape[0], -1))            # (B, T2, 2) = cat([yl, yh], 1)
-            rows = self.aux_convs[i - 1].run(cat)                              # (B, T2, 1), lrelu fused
+            if self.aux_convs is None:                                        # nn.AvgPool1d variant (hifigan.py:456-458,466)
+                rows = self.meanpools[i - 1].run(rows)
+            else:
+                cat = ops.DwtFn.apply(rows.reshape(rows.shape[0], -1))        # (B, T2, 2) = cat([yl, yh], 1)
+                rows = self.aux_convs[i - 1].run(cat)                          # (B, T2, 1), lrelu fused
             inputs.append(rows)
         par = y.is_cuda and _PARALLEL_STREAMS and len(self.discriminators) > 1
         if par:                                                               # the scales themselves are independent
@@ -711,7 +730,11 @@ class MultiScaleDiscriminator(nn.Module):
             return d.forward_rows(x)
 
         for i, d in enumerate(self.discriminators):
-            if par:
+            # a spectral-normed scale stays on the calling stream: its parameters receive their gradients through autograd
+            # (w / sigma is recomputed per forward), and with that chain on a side stream the gradient of the first layer's
+            # weight_orig was intermittently lost when the scale is used twice in one backward (profiles/r02_notes.md)
+            side = par and not (_SPECTRAL_ON_MAIN and any(getattr(l[0], "norm", "") == "spectral" for l in d.convs))
+            if side:
                 streams[i].wait_stream(cur)
                 with torch.cuda.stream(streams[i]):
                     y_d_r, fmap_r = run_scale(d, inputs[i])

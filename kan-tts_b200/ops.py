@@ -532,7 +532,13 @@ class ConvFn(torch.autograd.Function):
                                                  st), "kt_conv1d_bwd_data")
             _count(max(spec.stride if not spec.transposed else 1, spec.upsample))
         if ctx.has_resid and ctx.needs_input_grad[1]:
-            dres = dy_full
+            # NOT the incoming tensor itself: the autograd engine accumulates gradients arriving at the same input IN PLACE
+            # into the first arrival when it holds the last reference (input_buffer.cpp: can_accumulate_inplace), and
+            # `dy_full` is still being read -- by this layer's weight-gradient chain on its side stream and, when it is the
+            # shared output of Mean3Fn.backward, by the other parallel resblocks on THEIR streams.  Returning the alias let
+            # the engine overwrite it under those readers: parameter gradients of the generator were off by ~5 % with the
+            # (slow) exact-fp32 kernels and side streams on (profiles/r02_notes.md, scripts/diag_fullsize.py).
+            dres = dy_full.clone()
         dbias, dv, dg = _weight_backward(spec, d, x_, dy, y_, v, g, ctx.params, ctx.norm, ctx.needs_input_grad[3],
                                          ctx.has_g and ctx.needs_input_grad[4], ctx.has_bias and ctx.needs_input_grad[2])
         return dx, dres, dbias, dv, dg, None, None

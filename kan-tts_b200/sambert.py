@@ -443,17 +443,32 @@ class VarRnnARPredictor(nn.Module):
         return x, h_new
 
     def infer(self, cond, masks=None):
-        batch_size, length = cond.size(0), cond.size(1)
-        output = []
-        x = torch.zeros((batch_size, 1), device=cond.device)
-        h = None
-        for i in range(length):
-            x, h = self.forward(x.unsqueeze(1), cond[:, i: i + 1, :], h=h)
-            output.append(x)
-        output = torch.cat(output, dim=-1)
+        """adaptors.py:67-83: the per-symbol Python loop of the reference (prenet -> LSTM step -> fc, ~10 launches per symbol)
+        is ONE kernel (kt_ar_duration_infer: one CTA per batch item walks the recurrence); the condition's share of the
+        layer-0 input projection is one k = 1 conv over all symbols."""
+        from ._lib import load, check, ptr, stream_ptr
+        lstm, B, L = self.lstm, cond.size(0), cond.size(1)
+        H = lstm.hidden_size
+        fc1, fc2 = [m for m in self.prenet.fcs if isinstance(m, nn.Linear)][:2]
+        P1, P2 = fc1.out_features, fc2.out_features
+        if not cond.is_cuda:
+            raise RuntimeError("kantts_b200: VarRnnARPredictor.infer needs CUDA tensors (no CPU fallback)")
+        with torch.no_grad():
+            w_ih0 = lstm.weight_ih_l0
+            wc = w_ih0[:, P2:].contiguous().unsqueeze(-1)                       # (4H, cond_units, 1)
+            spec = self.__dict__.setdefault("_cond_spec", ops.ConvSpec(c_in=wc.shape[1], c_out=4 * H, kernel=1))
+            g0c = ops.conv(cond.contiguous(), spec, ops.PreparedWeight(), wc, None, (lstm.bias_ih_l0 + lstm.bias_hh_l0).contiguous())
+            out = torch.empty(B, L, device=cond.device, dtype=torch.float32)
+            t = lambda w: w.detach().t().contiguous()
+            args = (g0c, fc1.weight.detach()[:, 0].contiguous(), fc1.bias.detach(), t(fc2.weight), fc2.bias.detach(),
+                    t(w_ih0[:, :P2]), t(lstm.weight_hh_l0), t(lstm.weight_ih_l1), t(lstm.weight_hh_l1),
+                    (lstm.bias_ih_l1 + lstm.bias_hh_l1).detach().contiguous(), self.fc.weight.detach()[0].contiguous())
+            check(load().kt_ar_duration_infer(*[ptr(a) for a in args], float(self.fc.bias.detach()[0]), ptr(out), B, L, H, P1, P2,
+                                              stream_ptr()), "kt_ar_duration_infer")
+            ops._count(2)
         if masks is not None:
-            output = output.masked_fill(masks, 0.0)
-        return output
+            out = out.masked_fill(masks, 0.0)
+        return out
 
 
 class VarFsmnRnnNARPredictor(nn.Module):

@@ -19,6 +19,14 @@ for leg in "$@"; do
     graderr) timeout 300 python scripts/grad_err_report.py > gpurun_out/graderr_$TAG.log 2>&1; echo "graderr rc=$?" >> $S ;;
     torchgpu) timeout 600 python bench.py --impl torch_gpu --steps 5 --warmup 3 > gpurun_out/torchgpu_$TAG.log 2>&1; echo "torchgpu rc=$?" >> $S ;;
     rbtest) timeout 300 python scripts/rb_test.py > gpurun_out/rbtest_$TAG.log 2>&1; echo "rbtest rc=$?" >> $S; tail -3 gpurun_out/rbtest_$TAG.log >> $S ;;
+    diag) timeout 600 python scripts/diag_fullsize.py > gpurun_out/diag_$TAG.log 2>&1; echo "diag rc=$?" >> $S; grep -E "MSD|G grads|FFMA mel" gpurun_out/diag_$TAG.log >> $S ;;
+    diaglayers) timeout 600 python scripts/diag_layers.py > gpurun_out/diaglayers_$TAG.log 2>&1; echo "diaglayers rc=$?" >> $S ;;
+    diagmsd) timeout 600 python scripts/diag_layers.py msd > gpurun_out/diagmsd_$TAG.log 2>&1; echo "diagmsd rc=$?" >> $S ;;
+    diaggan) timeout 900 python scripts/diag_ganstep.py > gpurun_out/diaggan_$TAG.log 2>&1; echo "diaggan rc=$?" >> $S ;;
+    benchside) timeout 600 python bench.py --workload c1 --steps 20 --warmup 5 > gpurun_out/bench_c1_$TAG.log 2>&1; echo "bench c1 rc=$?" >> $S
+               timeout 900 python bench.py --workload c4 --steps 5 --warmup 3 > gpurun_out/bench_c4_$TAG.log 2>&1; echo "bench c4 rc=$?" >> $S ;;
+    ncu_wgrad) for LN in gen_32_32_k7 mpd_1024_1024_k5_p3; do
+           timeout 600 ncu --set full --clock-control none --import-source on -k regex:wgrad_tc_kernel -s 4 -c 1 -f -o gpurun_out/ncu_wgrad_${LN}_$TAG python scripts/layer_bench.py --only $LN --iters 2 > gpurun_out/ncu_wgrad_$TAG.log 2>&1; echo "ncu_wgrad $LN rc=$?" >> $S; done ;;
     *) echo "unknown leg $leg" >> $S ;;
   esac
 done

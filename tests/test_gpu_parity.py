@@ -317,9 +317,12 @@ def test_forward_pair_equals_two_calls(golden, name, cls):
                 (oa, fa), (ob, fb) = d.forward_pair(ya, yb, detach_b=True)
             assert not any(o.requires_grad for o in ob)
         sum((o * o).sum() for o in oa).backward()
+        K.hifigan.join_side_streams(torch.device(DEV))
+        torch.cuda.synchronize()
         res[mode] = ([o.detach().clone() for o in oa], [o.detach().clone() for o in ob],
                      [f.detach().clone() for fm in fa for f in fm], [f.detach().clone() for fm in fb for f in fm],
-                     ya.grad.clone(), {k: v.clone() for k, v in d.state_dict().items() if k.endswith(("weight_u", "weight_v"))})
+                     ya.grad.clone(), {k: v.clone() for k, v in d.state_dict().items() if k.endswith(("weight_u", "weight_v"))},
+                     {k: q.grad.clone() for k, q in d.named_parameters() if q.grad is not None})
     for mode in ("pair", "two_frozen", "pair_frozen"):
         for i in range(4):
             for a, b in zip(res["two"][i], res[mode][i]):
@@ -327,6 +330,9 @@ def test_forward_pair_equals_two_calls(golden, name, cls):
         assert rel_l2(res[mode][4], res["two"][4]) < 1e-4, (mode, rel_l2(res[mode][4], res["two"][4]))
         for k, v in res["two"][5].items():
             assert rel_l2(res[mode][5][k], v) < 1e-5, (mode, k)
+        for k, v in res["two"][6].items():                       # parameter gradients (only the un-frozen runs have any)
+            if k in res[mode][6]:
+                assert rel_l2(res[mode][6][k], v) < 1e-4, (mode, k, rel_l2(res[mode][6][k], v))
 
 
 def test_direct_grad_accumulation_matches_autograd(golden):
@@ -429,13 +435,17 @@ def test_full_size_c2_train_step_matches_oracle(force_ffma):
     ref = gan.train_step(y, x)
     for k in ("mel_loss", "adversarial_loss", "feature_matching_loss", "generator_loss", "real_loss", "fake_loss", "discriminator_loss"):
         assert abs(log[k] - ref[k]) <= 2e-4 * max(1.0, abs(ref[k])), (k, log[k], ref[k])
+    failures = []
     for tag, m, od in (("g", G, gan.g), ("msd", D["MultiScaleDiscriminator"], gan.d["MultiScaleDiscriminator"]),
                        ("mpd", D["MultiPeriodDiscriminator"], gan.d["MultiPeriodDiscriminator"])):
         refg = {k: od[k].grad for k, _ in m.named_parameters()}
         # full size: 131 072 output rows per weight gradient and ~100 LeakyReLUs upstream of every tensor -- the ~1e-5
         # forward difference flips the derivative mask of the pre-activations nearest zero (a discontinuous function of
         # the forward), which dominates the per-tensor figure (measured: -s output of this test)
-        _check_param_grads(m, refg, exact=False, tol=(1e-4, 1e-4, 2e-3) if force_ffma else (5e-3, 5e-3, 1e-1))
+        try:
+            _check_param_grads(m, refg, exact=False, tol=(1e-4, 1e-4, 2e-3) if force_ffma else (5e-3, 5e-3, 1e-1))
+        except AssertionError as e:
+            failures.append((tag, str(e)[:300]))
         sd = m.state_dict()
         num = den = 0.0
         for k, v in od.items():
@@ -445,6 +455,7 @@ def test_full_size_c2_train_step_matches_oracle(force_ffma):
             num += float(((sd[k].cpu() - v.detach()).double() ** 2).sum())
             den += float(((b - v.detach()).double() ** 2).sum())
         assert num <= 2e-2 * den, (tag, num, den)
+    assert not failures, failures
 
 
 RB_CASES = {
@@ -478,14 +489,23 @@ def test_fused_resblock_unit_vs_oracle(name):
         prm += [v, g, b]
     x = torch.randn(B, C, T, generator=gen)
     r = torch.randn(B, C, T, generator=gen)
-    # ---- oracle (CPU, channels-first)
-    ref_in = [t.clone().requires_grad_(True) for t in [x] + prm]
-    xo, v1, g1, b1, v2, g2, b2 = ref_in
-    w1 = g1 * v1 / v1.norm(2, dim=(1, 2), keepdim=True)
-    w2 = g2 * v2 / v2.norm(2, dim=(1, 2), keepdim=True)
-    ho = convref.conv_layer(xo, w1, b1, dilation=d, pad_left=p1, pad_right=(k - 1) * d - p1, act_in=0.1)
-    yo = convref.conv_layer(ho, w2, b2, resid=xo, dilation=1, pad_left=p2, pad_right=(k - 1) - p2, act_in=0.1)
-    (yo * r).sum().backward()
+    # ---- oracle (CPU, channels-first).  LeakyReLU is written as x * where(m > 0, 1, slope) with the mask source m given
+    # separately: m = the oracle's own value is the plain function; m = the PRODUCT's value of the same tensor gives the
+    # derivative on the product's side of every kink -- the two differ only where a pre-activation's sign differs, i.e. on
+    # the ~1e-5 fraction of elements whose magnitude is below the forward error (see the tolerances below)
+    def run_oracle(h_mask):
+        ref_in = [t.clone().requires_grad_(True) for t in [x] + prm]
+        xo, v1, g1, b1, v2, g2, b2 = ref_in
+        w1 = g1 * v1 / v1.norm(2, dim=(1, 2), keepdim=True)
+        w2 = g2 * v2 / v2.norm(2, dim=(1, 2), keepdim=True)
+        lre = lambda t, msk: t * torch.where(msk > 0, torch.ones(()), torch.full((), 0.1))
+        ho = convref.conv_layer(lre(xo, xo.detach()), w1, b1, dilation=d, pad_left=p1, pad_right=(k - 1) * d - p1)
+        yo = convref.conv_layer(lre(ho, ho.detach() if h_mask is None else h_mask), w2, b2, resid=xo, dilation=1, pad_left=p2,
+                                pad_right=(k - 1) - p2)
+        (yo * r).sum().backward()
+        return ref_in, ho.detach(), yo.detach()
+    ref_in, ho, yo = run_oracle(None)
+    xo = ref_in[0]
     # ---- product: the fused unit on channels-last rows
     dev_in = [torch.nn.Parameter(t.clone().to(DEV)) for t in prm]
     xg = x.permute(0, 2, 1).contiguous().to(DEV).requires_grad_(True)
@@ -495,10 +515,55 @@ def test_fused_resblock_unit_vs_oracle(name):
     y = ops.resblock(xg, s1, ops.PreparedWeight(), dev_in[0], dev_in[1], dev_in[2], s2, ops.PreparedWeight(), dev_in[3], dev_in[4],
                      dev_in[5], rd)
     assert ops.tc_launch_count() == n0 + 1                                  # ONE launch for the pair
-    assert rel_l2(y.detach().cpu().permute(0, 2, 1), yo.detach()) < 1e-4
+    assert rel_l2(y.detach().cpu().permute(0, 2, 1), yo) < 1e-4
     (y * r.permute(0, 2, 1).contiguous().to(DEV)).sum().backward()
     K.hifigan.join_side_streams(torch.device(DEV))
     torch.cuda.synchronize()
-    assert rel_l2(xg.grad.cpu().permute(0, 2, 1), xo.grad) < 2e-4
+    # the product's own intermediate (bit-identical to the fused kernel's, scripts/rb_test.py) as the mask source
+    with torch.no_grad():
+        h_dev = ops.conv(xg.detach(), s1, ops.PreparedWeight(), dev_in[0], dev_in[1], dev_in[2]).cpu().permute(0, 2, 1)
+    flipped = float(((h_dev > 0) != (ho > 0)).float().mean())
+    ref_m, _, _ = run_oracle(h_dev)
+    # (a) same side of every LeakyReLU kink: arithmetic parity of the gradient kernels
+    assert rel_l2(xg.grad.cpu().permute(0, 2, 1), ref_m[0].grad) < 2e-4, ("dx, product masks", flipped)
+    for got, want, nm in zip(dev_in, ref_m[1:], ("v1", "g1", "b1", "v2", "g2", "b2")):
+        assert rel_l2(got.grad.cpu(), want.grad) < 5e-4, (nm, rel_l2(got.grad.cpu(), want.grad))
+    # (b) against the plain oracle: each flipped element changes its gradient by the factor 1 / slope, so the
+    # relative difference is ~ sqrt(fraction flipped) -- 3e-3 for a 1e-5 fraction -- whatever the arithmetic precision
+    bound = 5e-4 + 3.0 * flipped ** 0.5
+    assert rel_l2(xg.grad.cpu().permute(0, 2, 1), xo.grad) < bound, (flipped, bound)
     for got, want, nm in zip(dev_in, ref_in[1:], ("v1", "g1", "b1", "v2", "g2", "b2")):
-        assert rel_l2(got.grad.cpu(), want.grad) < 1e-3, (nm, rel_l2(got.grad.cpu(), want.grad))
+        assert rel_l2(got.grad.cpu(), want.grad) < 2e-3 + 3.0 * flipped ** 0.5, (nm, rel_l2(got.grad.cpu(), want.grad))
+
+
+def test_msd_avgpool_variant_matches_oracle():
+    """MultiScaleDiscriminator(downsample_pooling="AvgPool1d") (hifigan.py:456-458,466: the class-default pooling, not used
+    by the shipped yamls) -- outputs, feature maps, input and parameter gradients vs the oracle."""
+    from oracle import hifigan as O
+    cfg = dict(scales=3, downsample_pooling="AvgPool1d", downsample_pooling_params={"kernel_size": 4, "stride": 2, "padding": 2},
+               discriminator_params=dict(in_channels=1, out_channels=1, kernel_sizes=[15, 41, 5, 3], channels=16,
+                                         max_downsample_channels=64, max_groups=4, bias=True, downsample_scales=[2, 2, 4, 4, 1],
+                                         nonlinear_activation="LeakyReLU", nonlinear_activation_params={"negative_slope": 0.1}),
+               follow_official_norm=False)
+    torch.manual_seed(11)
+    m = K.MultiScaleDiscriminator(**cfg)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    y = 0.3 * torch.randn(2, 1, 4096)
+    yo = y.clone().requires_grad_(True)
+    leaf = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    outs_o, fm_o = O.msd_forward(leaf, yo, True, **cfg)
+    sum((o * o).sum() for o in outs_o).backward()
+    m = m.to(DEV).train()
+    yg = y.to(DEV).requires_grad_(True)
+    outs, fm = m(yg)
+    sum((o * o).sum() for o in outs).backward()
+    K.hifigan.join_side_streams(torch.device(DEV))
+    torch.cuda.synchronize()
+    for a, b in zip(outs, outs_o):
+        assert a.shape == b.shape and rel_l2(a.detach().cpu(), b.detach()) < 1e-4
+    for fa, fb in zip(fm, fm_o):
+        for a, b in zip(fa, fb):
+            assert a.shape == b.shape and rel_l2(a.detach().cpu(), b.detach()) < 1e-4
+    assert rel_l2(yg.grad.cpu(), yo.grad) < 5e-4
+    for k, p in m.named_parameters():
+        assert rel_l2(p.grad.cpu(), leaf[k].grad) < 2e-3, k
