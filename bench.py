@@ -137,7 +137,8 @@ def reference_main(args, rank):
             "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": B_PER_GPU * args.gpus, "segment": T_WAV,
-                       "note": "CPU arm: each step is a bounded sample of the workload, see cpu_baseline.sample"},
+                       "note": "CPU arm: one process on the host cores whatever N is; each step = cpu_baseline.sample "
+                               "(the full 16-segment batch by default)"},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -311,7 +312,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c1", "c4"],
                     help="c2 (default, the headline: BASELINE configs[1]); c1: generator forward B = 1 (configs[0]); c4: SAM-BERT "
                          "train step B = 32 x 256 symbols x 768 frames (configs[3]) -- informational lines with their own metric")
-    ap.add_argument("--cpu-sample-batch", type=int, default=4)
+    ap.add_argument("--cpu-sample-batch", type=int, default=16,
+                    help="segments per CPU step (16 = the full batch of the workload: same config as the CUDA arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--launch", default="auto", choices=["auto", "graph", "eager"],

@@ -18,6 +18,8 @@
 // 5 MMA issuer, 6-9 epilogue 1 (TMEM -> +b1 -> [h to global] -> lrelu -> split -> H image), 14-17 epilogue 2
 // (TMEM -> +b2 -> transposition -> +x -> y).  The MMA issuer software-pipelines  c1(i+1) | c2(i)  so that the tensor
 // pipe runs the next tile's first conv while epilogue 1 builds this tile's H image.
+#include <cuda.h>   // CUtensorMap + the cuTensorMapEncodeTiled prototype (resolved at run time, no link dependency)
+
 #include <algorithm>
 #include <atomic>
 #include <vector>
@@ -51,6 +53,14 @@ struct RbParams {
   int last_kslices;                 // K = 16 slices of the last step (pair with odd k: 2, else 4)
   int resident, nb;                 // weights: all tiles resident | ring of nb stages
   int tile_bytes;                   // one weight tile: [hi NT rows | lo NT rows] x 128 B
+  // TMA-staged input (north_star: "TMA-staged input tiles"): the fp32 x tile [rows_box][C] of every tile -- halo included,
+  // rows outside [0, T) zero-filled by the TMA unit itself -- is brought into shared memory with cp.async.bulk.tensor (one
+  // box of 32 channels x rows_box rows per 32 channels); the producer warps then only CONVERT shared -> shared
+  // (LeakyReLU, hi / lo split, swizzled image): no global-load latency, no address arithmetic, no bounds tests.
+  int tma;                          // 1: x tiles arrive by TMA (f stages = nx); 0: producer warps load them (LDG)
+  int rows_box;                     // rows of one TMA box (rows_x, + d1 for the paired layout)
+  int fstage_bytes;                 // one fp32 landing stage: (C / 32) boxes x rows_box x 128 B
+  alignas(64) CUtensorMap tmx;      // 3-D map of x: (C, T, B), box (32, rows_box, 1), no swizzle, zero OOB fill
 };
 
 // ---- weight packing for the paired (C = 32) layout: tile p = taps (2p, 2p + 1) along K -----------------------------
@@ -148,6 +158,38 @@ __device__ __forceinline__ void rb_store32(float* stg, int lane, const float (&v
   }
 }
 
+// ---- TMA: one box (32 channels x rows) of the 3-D tensor (C, T, B) -> shared memory, completion on an mbarrier (SASS UTMALDG)
+__device__ __forceinline__ void tma_load_box(void* dst_smem, const CUtensorMap* map, int c0, int t0, int b, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(t0), "r"(b)
+      : "memory");
+}
+
+// ---- shared fp32 landing tile -> split-bf16 SWIZZLE_128B image (fused LeakyReLU), rows [r_begin, r_end), 128 threads.
+// ft: boxes of [rows_box][32 floats] (128-byte rows, linear).  PAIR (C = 32): image row r = [x[r] | x[r + d]];
+// else (C = 64): image row r = channels 0..63 of row r, box q / 4.  Rows outside [0, T) arrive as zeros.
+template <bool PAIR>
+__device__ __forceinline__ void rb_convert_tile(uint8_t* img_hi, uint8_t* img_lo, const float* ft, int box_floats, int d, float slope,
+                                                int r_begin, int r_end, int tid) {
+  const int q = tid & 7;
+  const float* base = PAIR ? ft + (q >> 2) * d * 32 + (q & 3) * 8 : ft + (q >> 2) * box_floats + (q & 3) * 8;
+#pragma unroll 2
+  for (int r = r_begin + (tid >> 3); r < r_end; r += 16) {
+    const float4 a = *reinterpret_cast<const float4*>(base + r * 32);
+    const float4 b = *reinterpret_cast<const float4*>(base + r * 32 + 4);
+    float e[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int z = 0; z < 8; ++z) e[z] = e[z] > 0.f ? e[z] : e[z] * slope;
+    uint4 hi, lo;
+    split8(e, hi, lo);
+    const uint32_t o = sw128_offset((uint32_t)r, (uint32_t)q);
+    *reinterpret_cast<uint4*>(img_hi + o) = hi;
+    *reinterpret_cast<uint4*>(img_lo + o) = lo;
+  }
+}
+
 __global__ void __launch_bounds__(kRbThreads, 1) resblock_tc_kernel(const __grid_constant__ RbParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -157,7 +199,8 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_tc_kernel(const __grid
   uint8_t* x_base = smem;                                            // nx stages x (hi | lo)
   uint8_t* h_base = x_base + (size_t)p.nx * 2 * ximg;                // (hi | lo)
   uint8_t* w_base = h_base + 2 * (size_t)himg;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(w_base + (size_t)nslots * p.tile_bytes);
+  uint8_t* f_base = w_base + (size_t)nslots * p.tile_bytes;          // fp32 landing stages of the TMA-staged x tiles (tma only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(f_base + (p.tma ? (size_t)p.nx * p.fstage_bytes : 0));
   uint64_t* x_full = bars;                 // [2]
   uint64_t* x_empty = x_full + 2;          // [2]
   uint64_t* a1_full = x_empty + 2;         // [2]
@@ -168,7 +211,8 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_tc_kernel(const __grid
   uint64_t* h_empty = h_full + 1;          // [1]
   uint64_t* w_full = h_empty + 1;          // [nslots]
   uint64_t* w_empty = w_full + nslots;     // [nslots] (ring only)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty + nslots);
+  uint64_t* f_full = w_empty + nslots;     // [2] (tma only): the x tile has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(f_full + 2);
   float* epi_stage = reinterpret_cast<float*>(tmem_slot + 4);        // 8 warps x 32 rows x 16 fp32
   float* s_bias = epi_stage + 8 * 32 * 16;                           // b1 | b2 (2 * NT floats)
 
@@ -179,7 +223,8 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_tc_kernel(const __grid
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&x_full[s], 128); mbar_init(&x_empty[s], 1);
+      mbar_init(&x_full[s], p.tma ? 256 : 128); mbar_init(&x_empty[s], 1);
+      mbar_init(&f_full[s], 1);
       mbar_init(&a1_full[s], 1); mbar_init(&a1_empty[s], 128);
       mbar_init(&a2_full[s], 1); mbar_init(&a2_empty[s], 128);
     }
@@ -203,6 +248,37 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_tc_kernel(const __grid
     // ===================== producers: x images (fused input LeakyReLU) =====================
     const int pg = warp < 4 ? 0 : 1;
     const int ptid = warp < 4 ? tid : tid - 320;
+    if (p.tma) {
+      // TMA-staged: both groups convert the landed fp32 tile cooperatively (upper / lower half of the image rows); thread 0
+      // of group 0 issues the loads, `nx` tiles ahead, as soon as the landing stage has been read
+      const int split = ((p.rows_x / 2) + 15) & ~15;
+      const int r0 = pg ? min(split, p.rows_x) : 0, r1 = pg ? p.rows_x : min(split, p.rows_x);
+      const int nbox = p.c / 32, box_floats = p.rows_box * 32;
+      auto issue = [&](int ti) {
+        const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+        const int bb = tile / p.tiles_per_item, it = tile - bb * p.tiles_per_item;
+        const int x0 = it * p.to - p.p2 - p.p1;
+        const int s = ti % p.nx;
+        mbar_arrive_expect_tx(&f_full[s], (uint32_t)p.fstage_bytes);
+        for (int bx = 0; bx < nbox; ++bx)
+          tma_load_box(f_base + (size_t)s * p.fstage_bytes + (size_t)bx * box_floats * 4, &p.tmx, bx * 32, x0, bb, &f_full[s]);
+      };
+      if (pg == 0 && ptid == 0)
+        for (int ti = 0; ti < min(p.nx, ntile_cta); ++ti) issue(ti);
+      for (int ti = 0; ti < ntile_cta; ++ti) {
+        const int s = ti % p.nx, n = ti / p.nx;
+        mbar_wait(&x_empty[s], (uint32_t)((n & 1) ^ 1));
+        mbar_wait(&f_full[s], (uint32_t)(n & 1));
+        uint8_t* img_hi = x_base + (size_t)s * 2 * ximg;
+        const float* ft = reinterpret_cast<const float*>(f_base + (size_t)s * p.fstage_bytes);
+        if (p.pair) rb_convert_tile<true>(img_hi, img_hi + ximg, ft, box_floats, p.d1, p.slope, r0, r1, ptid);
+        else rb_convert_tile<false>(img_hi, img_hi + ximg, ft, box_floats, p.d1, p.slope, r0, r1, ptid);
+        fence_proxy_async();
+        mbar_arrive(&x_full[s]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // every producer thread has read the landing stage
+        if (pg == 0 && ptid == 0 && ti + p.nx < ntile_cta) issue(ti + p.nx);
+      }
+    } else {
     const Side sx{p.x, nullptr, SIDE_LRELU, p.slope};
     for (int ti = 0; ti < ntile_cta; ++ti) {
       // two stages: the groups own one stage each (alternate tiles).  One stage: group 0 alone -- two groups waiting on the
@@ -223,6 +299,7 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_tc_kernel(const __grid
       }
       fence_proxy_async();
       mbar_arrive(&x_full[s]);
+    }
     }
   } else if (warp == 4) {
     // ===================== weight stream =====================
@@ -467,9 +544,15 @@ struct RbPlan {
   size_t smem;
 };
 
-static int rb_fixed_smem(int nslots) { return (14 + 2 * nslots) * 8 + 16 + 8 * 2048 + 2 * 64 * 4; }
+static int rb_fixed_smem(int nslots) { return (16 + 2 * nslots) * 8 + 16 + 8 * 2048 + 2 * 64 * 4; }
 
-static RbPlan rb_plan(const KtResblockDesc* d) {
+// KANTTS_B200_RB_TMA=0 keeps the producer warps on global loads (A/B testing); default: TMA-staged x tiles when they fit
+static bool rb_want_tma() {
+  static const bool v = [] { const char* e = getenv("KANTTS_B200_RB_TMA"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
+static RbPlan rb_plan(const KtResblockDesc* d, bool tma = false) {
   RbPlan pl{};
   RbParams& p = pl.p;
   if (d->path == KT_PATH_FFMA) return pl;
@@ -488,7 +571,12 @@ static RbPlan rb_plan(const KtResblockDesc* d) {
   p.rows_x = (kRbM + span1 + 7) & ~7;
   p.rows_h = (kRbM + span2 + 7) & ~7;
   p.tile_bytes = 2 * p.c * 128;
-  const int ximg2 = 2 * p.rows_x * 128, himg2 = 2 * p.rows_h * 128;
+  const int himg2 = 2 * p.rows_h * 128;
+  p.rows_box = p.rows_x + (p.pair ? p.d1 : 0);
+  p.fstage_bytes = (p.c / 32) * p.rows_box * 128;
+  if (tma && p.rows_box > 256) return pl;          // TMA box limit
+  p.tma = tma ? 1 : 0;
+  const int ximg2 = 2 * p.rows_x * 128 + (tma ? p.fstage_bytes : 0);   // one x stage: (hi | lo) image (+ its fp32 landing stage)
   const int cap = kMaxDynSmem - 1024;
   // preference: resident weights + 2 x stages; resident + 1; ring (>= 3 stages) + 2 x stages; ring + 1
   const int res_bytes = 2 * p.nsteps * p.tile_bytes;
@@ -535,15 +623,39 @@ int resblock_pack(const KtResblockDesc* d, const float* w, void* img, cudaStream
   return tc_pack_layer(&cd, 0, w, img, st);
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {   // driver entry point through the runtime: libkantts has no link-time libcuda dependency
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
 int resblock_fwd(const KtResblockDesc* d, const float* x, const void* img1, const float* b1, const void* img2, const float* b2,
                  float* h, float* y, cudaStream_t st) {
-  RbPlan pl = rb_plan(d);
+  RbPlan pl = rb_plan(d, rb_want_tma() && encode_tiled_fn() != nullptr);
+  if (!pl.ok) pl = rb_plan(d, false);
   KT_REQUIRE(pl.ok, "resblock_fwd: shape not supported by the fused kernel (channels 32 / 64, odd kernel)");
   KT_REQUIRE(x && img1 && img2 && y, "resblock_fwd: null pointer");
   RbParams& p = pl.p;
   p.x = x; p.y = y; p.h = h;
   p.w1 = reinterpret_cast<const __nv_bfloat16*>(img1); p.w2 = reinterpret_cast<const __nv_bfloat16*>(img2);
   p.b1 = b1; p.b2 = b2;
+  if (p.tma) {
+    const cuuint64_t gdim[3] = {(cuuint64_t)p.c, (cuuint64_t)p.t, (cuuint64_t)p.batch};
+    const cuuint64_t gstr[2] = {(cuuint64_t)p.c * 4, (cuuint64_t)p.t * p.c * 4};
+    const cuuint32_t box[3] = {32, (cuuint32_t)p.rows_box, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode_tiled_fn()(&p.tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(x), gdim, gstr, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    KT_REQUIRE(r == CUDA_SUCCESS, "resblock_fwd: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  }
   static std::atomic<bool> cfg{false};
   if (!cfg.load(std::memory_order_acquire)) {
     KT_CHECK_CUDA(cudaFuncSetAttribute(resblock_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
