@@ -50,34 +50,38 @@ constexpr int kTcMaxGroups = 8;  // residue classes (= input step) per phase
 // layer (8 -> 16 channels per group) becomes 2 tiles of K = 64 x N = 128 instead of 16 tiles of K = 8 (padded to
 // 16) x N = 16 -- 8x fewer tiles, each restaging the activations once, at MMA shapes the tensor pipe runs well.
 // w is then [taps][kin_g][N] (rows = channels of ONE group) and K = gt * kin_g; kin_g = 0 means dense.
+// One thread = one 16-byte chunk (8 consecutive k) of one tile row r: the 8 source loads are coalesced across the warp (lanes =
+// consecutive produced channels n), the hi / lo chunks are written with two 16-byte stores (round 1 wrote single bf16
+// elements: 2-byte scattered stores and five 64-bit divisions per element made this the 4th largest kernel of the step).
 __global__ void tc_pack_weights_kernel(const float* __restrict__ w, int taps, int K, int N, int NT, int n_stride,
                                        int ntiles, int kin_g, int pout_g, __nv_bfloat16* __restrict__ out) {
   const int kchunks = (K + kTcKC - 1) / kTcKC;
-  const long long total = (long long)taps * kchunks * ntiles * NT * kTcKC;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % kTcKC);
-    const int r = (int)((i / kTcKC) % NT);
-    const long long block = i / ((long long)kTcKC * NT);
-    const int nt = (int)(block % ntiles);
-    const int kc = (int)((block / ntiles) % kchunks);
-    const int j = (int)(block / ((long long)ntiles * kchunks));
-    const int k = kc * kTcKC + c;
+  const int block = blockIdx.x;                                   // (j, kc, nt)
+  const int nt = block % ntiles, kc = (block / ntiles) % kchunks, j = block / (ntiles * kchunks);
+  uint8_t* tile = reinterpret_cast<uint8_t*>(out) + (size_t)block * (2u * NT * kTcKC * 2u);
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < NT * 8; idx += gridDim.y * blockDim.x) {
+    const int q = idx / NT, r = idx - q * NT;
     const int n = nt * n_stride + r;
-    bool ok = k < K && r < n_stride && n < N;
-    long long src;
-    if (kin_g > 0) {   // block diagonal: contraction channel k and produced channel r must be in the same group
-      ok = ok && (k / kin_g) == (r / pout_g);
-      src = ((long long)j * kin_g + (k % kin_g)) * N + n;
-    } else {
-      src = ((long long)j * K + k) * N + n;
+    const bool row_ok = r < n_stride && n < N;
+    float x[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kc * kTcKC + q * 8 + e;
+      bool ok = row_ok && k < K;
+      long long src;
+      if (kin_g > 0) {   // block diagonal: contraction channel k and produced channel r must be in the same group
+        ok = ok && (k / kin_g) == (r / pout_g);
+        src = ((long long)j * kin_g + (k % kin_g)) * N + n;
+      } else {
+        src = ((long long)j * K + k) * N + n;
+      }
+      x[e] = ok ? __ldg(w + src) : 0.f;
     }
-    const float x = ok ? w[src] : 0.f;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-    const long long base = block * (2LL * NT * kTcKC);
-    const uint32_t off = (sw128_offset((uint32_t)r, (uint32_t)(c >> 3)) >> 1) + (uint32_t)(c & 7);
-    out[base + off] = hi;
-    out[base + (long long)NT * kTcKC + off] = lo;
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    const uint32_t o = sw128_offset((uint32_t)r, (uint32_t)q);
+    *reinterpret_cast<uint4*>(tile + o) = hi;
+    *reinterpret_cast<uint4*>(tile + (size_t)NT * kTcKC * 2 + o) = lo;
   }
 }
 
@@ -689,10 +693,9 @@ long long tc_image_bytes(const KtConv1dDesc* d, int dir) {
 int tc_pack_layer(const KtConv1dDesc* d, int dir, const float* w, void* out, cudaStream_t st) {
   KT_REQUIRE(w && out && tc_plan(d, dir) > 0, "tc_pack_layer: layer not supported by the tcgen05 path");
   const TcLayerPlan L = layer_plan(d, dir);
-  const long long total = (long long)d->kernel * L.kchunks * L.ntiles * L.NT * kTcKC;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
-  tc_pack_weights_kernel<<<blocks, 256, 0, st>>>(w, d->kernel, L.kg, L.n_total, L.NT, L.n_stride, L.ntiles,
-                                                 L.grouped ? L.kin_g : 0, L.pout_g, reinterpret_cast<__nv_bfloat16*>(out));
+  const dim3 grid((unsigned)(d->kernel * L.kchunks * L.ntiles), (unsigned)ceil_div(L.NT * 8, 256));
+  tc_pack_weights_kernel<<<grid, 256, 0, st>>>(w, d->kernel, L.kg, L.n_total, L.NT, L.n_stride, L.ntiles,
+                                               L.grouped ? L.kin_g : 0, L.pout_g, reinterpret_cast<__nv_bfloat16*>(out));
   KT_CHECK_CUDA(cudaGetLastError());
   return KT_OK;
 }
@@ -714,7 +717,7 @@ void debug_set_trace(long long* dev_buf) { g_trace = dev_buf; }
 static int run_tc(TcParams p, cudaStream_t st) {   // p: phases already planned by plan_launches
   p.trace = g_trace;
   p.dbg = g_dbg;
-  p.fuse2 = (p.NT <= 64 && p.NT % 32 == 0) ? 1 : 0;   // NT = 128: same MMA floor either way (192 cycles per K slice), half the TMEM reads in the epilogue
+  p.fuse2 = (p.NT <= 128 && p.NT % 32 == 0) ? 1 : 0;   // [a_hi*b_hi | a_hi*b_lo] as one N = 2*NT MMA: A is read from shared memory once for both products
   p.tmem_cols = 32;
   while (p.tmem_cols < (p.fuse2 ? 2 : 1) * p.NT) p.tmem_cols <<= 1;
   p.tmem_cols *= 2;                                   // two accumulator buffers

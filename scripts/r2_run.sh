@@ -27,6 +27,7 @@ for leg in "$@"; do
                timeout 900 python bench.py --workload c4 --steps 5 --warmup 3 > gpurun_out/bench_c4_$TAG.log 2>&1; echo "bench c4 rc=$?" >> $S ;;
     ncu_wgrad) for LN in gen_32_32_k7 mpd_1024_1024_k5_p3; do
            timeout 600 ncu --set full --clock-control none --import-source on -k regex:wgrad_tc_kernel -s 4 -c 1 -f -o gpurun_out/ncu_wgrad_${LN}_$TAG python scripts/layer_bench.py --only $LN --iters 2 > gpurun_out/ncu_wgrad_$TAG.log 2>&1; echo "ncu_wgrad $LN rc=$?" >> $S; done ;;
+    ncu_rb) timeout 600 ncu --set full --clock-control none --import-source on -k regex:resblock_tc_kernel -s 2 -c 1 -f -o gpurun_out/ncu_resblock_$TAG env RB_ONLY_BIG=1 python scripts/rb_test.py > gpurun_out/ncu_rb_$TAG.log 2>&1; echo "ncu_rb rc=$?" >> $S ;;
     *) echo "unknown leg $leg" >> $S ;;
   esac
 done
