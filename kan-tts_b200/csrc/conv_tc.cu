@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           rm.base_row = (long long)bb * p.t_in * p.nsub;
           rm.fv0 = f0 + p.grp_qlo[g] * p.nsub;
           rm.nsub = p.nsub; rm.step = p.i_step; rm.rho = p.grp_rho[g]; rm.up = p.up; rm.t_lim = p.t_in * p.up;
+          if (!(p.dbg & 32) || it < p.na_stages)   // (ablation 32: images staged only on the first ring pass)
           stage_rows<5, SIMPLE, 3>(img_hi, img_hi + img_bytes, p.in, p.in.p, p.in.aux, p.c_in, ch_base + c * kTcKC,
                                 min(kTcKC, p.kg - c * kTcKC), false, rm, p.rows, ptid);
           fence_proxy_async();
@@ -250,6 +251,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             mbar_wait(&empty_b[s], ((it / p.nb_stages) & 1) ^ 1);
             const long long block = ((long long)p.tap_j[n] * p.kchunks + c) * p.ntiles + nt;
             const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wimg) + block * (long long)b_stage_bytes;
+            if ((p.dbg & 16) && it >= p.nb_stages) { mbar_arrive(&full_b[s]); continue; }   // ablation: no weight traffic after the first ring pass
             mbar_arrive_expect_tx(&full_b[s], (uint32_t)b_stage_bytes);
             bulk_g2s(b_base + (size_t)s * b_stage_bytes, src, (uint32_t)b_stage_bytes, &full_b[s]);
           }
@@ -307,7 +309,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                 mbar_wait(&full_b[sb], (uint32_t)((it_b / p.nb_stages) & 1));
               }
               const uint32_t b_hi = b_base16 + (uint32_t)sb * b_stage16;
-              if (fuse2) {
+              if (p.dbg & 64) {
+                // ablation: no MMAs (pipelines and commits only)
+              } else if (fuse2) {
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                   if (kk < kslices) {
