@@ -18,7 +18,6 @@
 // 5 MMA issuer, 6-9 epilogue 1 (TMEM -> +b1 -> [h to global] -> lrelu -> split -> H image), 14-17 epilogue 2
 // (TMEM -> +b2 -> transposition -> +x -> y).  The MMA issuer software-pipelines  c1(i+1) | c2(i)  so that the tensor
 // pipe runs the next tile's first conv while epilogue 1 builds this tile's H image.
-#include <cuda.h>   // CUtensorMap + the cuTensorMapEncodeTiled prototype (resolved at run time, no link dependency)
 
 #include <algorithm>
 #include <atomic>
@@ -26,6 +25,7 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tma.cuh"
 
 namespace kt {
 
@@ -621,19 +621,6 @@ int resblock_pack(const KtResblockDesc* d, const float* w, void* img, cudaStream
   cd.kernel = d->kernel; cd.stride = 1; cd.dilation = 1; cd.pad_left = d->kernel - 1; cd.upsample = 1; cd.path = KT_PATH_TC;
   int tc_pack_layer(const KtConv1dDesc*, int, const float*, void*, cudaStream_t);
   return tc_pack_layer(&cd, 0, w, img, st);
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {   // driver entry point through the runtime: libkantts has no link-time libcuda dependency
-  static EncodeTiledFn fn = [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
-    return reinterpret_cast<EncodeTiledFn>(f);
-  }();
-  return fn;
 }
 
 int resblock_fwd(const KtResblockDesc* d, const float* x, const void* img1, const float* b1, const void* img2, const float* b2,

@@ -16,10 +16,12 @@
 // with plain 16-byte stores and a second kernel reduces over the splits (cheaper than ~10^7 atomics).
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tma.cuh"
 
 namespace kt {
 
@@ -62,6 +64,71 @@ struct WgTcParams {
   int bias_grp;
   long long bias_off, split_stride;
 };
+
+// TMEM -> workspace partial tiles (warps 0-3 of either kernel; thread = accumulator row)
+__device__ __forceinline__ void wg_epilogue(const WgTcParams& p, uint64_t* tmem_full, uint32_t tmem_acc, int warp, int lane, int cb_tile,
+                                            int ca_tile, int cgrp, int u0, int nu, int split, bool has_bias) {
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;  // M index inside the unit
+    const uint32_t t_lane = tmem_acc + ((uint32_t)(warp * 32) << 16);
+    for (int u = 0; u < nu; ++u) {
+      int tap_n, ca_idx;
+      bool valid;
+      if (p.mode == 0) { tap_n = p.unit_tap0[u0 + u]; ca_idx = ca_tile * 128 + row; valid = true; }
+      else { tap_n = p.unit_tap0[u0 + u] + (row >> 6); ca_idx = row & 63; valid = (row >> 6) < p.unit_ntaps[u0 + u]; }
+      valid = valid && ca_idx < p.ca_g;
+      const int col0 = cb_tile * p.NT;                                    // first column inside the (super-)group
+      // columns [c_lo, c_hi) of this tile are stored, column n at obase + n
+      int c_lo = 0, c_hi = min(p.NT, p.cb_g - col0);
+      long long obase = 0;
+      if (valid) {
+        if (p.gt > 1) {   // block diagonal: row of conv group gl keeps only that group's cb_g0 columns
+          const int gl = ca_idx / p.ca_g0, ci_l = ca_idx - gl * p.ca_g0;
+          c_lo = gl * p.cb_g0; c_hi = c_lo + p.cb_g0;
+          obase = (long long)split * p.split_stride + (((long long)p.tap_j[tap_n]) * p.ca_g0 + ci_l) * p.cb +
+                  ((long long)cgrp * p.gt + gl) * p.cb_g0 - c_lo;
+        } else {
+          obase = (long long)split * p.split_stride + (((long long)p.tap_j[tap_n]) * p.ca_g + ca_idx) * p.cb + (long long)cgrp * p.cb_g + col0;
+        }
+      }
+      const bool vec = ((p.cb | p.cb_g0) & 3) == 0;
+      for (int n0 = 0; n0 < p.NT; n0 += 32) {
+        uint32_t rr[32];
+        tmem_ld32(t_lane + (uint32_t)(u * p.NT + n0), rr);
+        tmem_ld_wait();
+        if (valid) {
+          const int e0 = max(0, c_lo - n0), e1 = min(32, c_hi - n0);
+          if (vec) {   // (fully unrolled with predicates: rr[] must stay in registers)
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              if (e >= e0 && e < e1)
+                *reinterpret_cast<float4*>(p.ws + obase + n0 + e) =
+                    make_float4(__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (e >= e0 && e < e1) p.ws[obase + n0 + e] = __uint_as_float(rr[e]);
+          }
+        }
+      }
+    }
+    if (has_bias && warp == 0) {   // accumulator unit `nu`: every row = column sums; row 0 (lane 0) stores them
+      const int col0 = cb_tile * p.NT;
+      const int ncol = min(p.NT, p.cb_g - col0);
+      float* dst = p.ws + (long long)split * p.split_stride + p.bias_off + (long long)cgrp * p.cb_g + col0;
+      for (int n0 = 0; n0 < p.NT; n0 += 32) {
+        uint32_t rr[32];
+        tmem_ld32(tmem_acc + (uint32_t)(nu * p.NT + n0), rr);
+        tmem_ld_wait();
+        if (lane == 0) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (n0 + e < ncol) dst[n0 + e] = __uint_as_float(rr[e]);
+        }
+      }
+    }
+}
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -162,68 +229,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     }
 
     // ===================== epilogue (warps 0-3): TMEM -> workspace partial tiles =====================
-    if (warp < 4) {
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const int row = warp * 32 + lane;  // M index inside the unit
-    const uint32_t t_lane = tmem_acc + ((uint32_t)(warp * 32) << 16);
-    for (int u = 0; u < nu; ++u) {
-      int tap_n, ca_idx;
-      bool valid;
-      if (p.mode == 0) { tap_n = p.unit_tap0[u0 + u]; ca_idx = ca_tile * 128 + row; valid = true; }
-      else { tap_n = p.unit_tap0[u0 + u] + (row >> 6); ca_idx = row & 63; valid = (row >> 6) < p.unit_ntaps[u0 + u]; }
-      valid = valid && ca_idx < p.ca_g;
-      const int col0 = cb_tile * p.NT;                                    // first column inside the (super-)group
-      // columns [c_lo, c_hi) of this tile are stored, column n at obase + n
-      int c_lo = 0, c_hi = min(p.NT, p.cb_g - col0);
-      long long obase = 0;
-      if (valid) {
-        if (p.gt > 1) {   // block diagonal: row of conv group gl keeps only that group's cb_g0 columns
-          const int gl = ca_idx / p.ca_g0, ci_l = ca_idx - gl * p.ca_g0;
-          c_lo = gl * p.cb_g0; c_hi = c_lo + p.cb_g0;
-          obase = (long long)split * p.split_stride + (((long long)p.tap_j[tap_n]) * p.ca_g0 + ci_l) * p.cb +
-                  ((long long)cgrp * p.gt + gl) * p.cb_g0 - c_lo;
-        } else {
-          obase = (long long)split * p.split_stride + (((long long)p.tap_j[tap_n]) * p.ca_g + ca_idx) * p.cb + (long long)cgrp * p.cb_g + col0;
-        }
-      }
-      const bool vec = ((p.cb | p.cb_g0) & 3) == 0;
-      for (int n0 = 0; n0 < p.NT; n0 += 32) {
-        uint32_t rr[32];
-        tmem_ld32(t_lane + (uint32_t)(u * p.NT + n0), rr);
-        tmem_ld_wait();
-        if (valid) {
-          const int e0 = max(0, c_lo - n0), e1 = min(32, c_hi - n0);
-          if (vec) {   // (fully unrolled with predicates: rr[] must stay in registers)
-#pragma unroll
-            for (int e = 0; e < 32; e += 4)
-              if (e >= e0 && e < e1)
-                *reinterpret_cast<float4*>(p.ws + obase + n0 + e) =
-                    make_float4(__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3]));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (e >= e0 && e < e1) p.ws[obase + n0 + e] = __uint_as_float(rr[e]);
-          }
-        }
-      }
-    }
-    if (has_bias && warp == 0) {   // accumulator unit `nu`: every row = column sums; row 0 (lane 0) stores them
-      const int col0 = cb_tile * p.NT;
-      const int ncol = min(p.NT, p.cb_g - col0);
-      float* dst = p.ws + (long long)split * p.split_stride + p.bias_off + (long long)cgrp * p.cb_g + col0;
-      for (int n0 = 0; n0 < p.NT; n0 += 32) {
-        uint32_t rr[32];
-        tmem_ld32(tmem_acc + (uint32_t)(nu * p.NT + n0), rr);
-        tmem_ld_wait();
-        if (lane == 0) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (n0 + e < ncol) dst[n0 + e] = __uint_as_float(rr[e]);
-        }
-      }
-    }
-    }
+    if (warp < 4) wg_epilogue(p, tmem_full, tmem_acc, warp, lane, cb_tile, ca_tile, cgrp, u0, nu, split, has_bias);
     tc_fence_before();
   } else if (warp == 5) {
     // ===================== MMA issuer =====================
@@ -279,6 +285,195 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
   }
 }
 
+// ---- TMA-fed variant (plain convs, no nearest-upsampling, channel counts % 8 == 0) -------------------------------------
+// The register-staged kernel above is bound by its producers: every CTA converts its fp32 operand rows to split bf16
+// itself (a 1024-channel layer converts each element ~23 times, once per (channel tile, unit group) CTA) with ~2 loads
+// in flight per thread -- 11 us per 64-row chunk against 1.6 us of MMAs (call r2y).  Here one elementwise pre-pass writes
+// each operand ONCE as hi / lo bf16 planes ([plane][batch][time][sub-sequence][channel], the activation layout), and the
+// weight-gradient CTAs pull their tiles with cp.async.bulk.tensor (SWIZZLE_128B boxes of 64 channels x `nsub` x `tt`
+// time steps land as exactly the MN-major images the MMAs read; rows outside [0, T) are the TMA unit's zero fill), so the
+// main loop is one elected producer thread, one elected MMA thread and an `nstages`-deep mbarrier ring.
+// A chunk = `tt` base time steps x all sub-sequences = R rows, padded to Rp = ceil16(R) (K = 16 per MMA) with rows that
+// are zeroed once and never written again.  A strided conv reads one residue class of the input per unit group: each
+// residue rho has its own tensor map (base + rho rows, time stride = step), so no element strides are needed.
+constexpr int kWgTmaThreads = 192;   // warps 0-3 epilogue, 4 TMEM alloc + TMA producer, 5 MMA issuer
+constexpr int kWgTmaMaxStages = 4;
+
+struct WgTmaExtra {
+  int tt, R, Rp, nstages;
+  int rows_a_p;        // rows of one A image plane (multiple of 8): Rp + tap span
+  int a_box_t;         // time steps per A box = tt + (largest tap span of a unit group)
+  int chunks_per_batch;
+  alignas(64) CUtensorMap map_b;
+  alignas(64) CUtensorMap map_a[8];   // one per residue class of the input
+};
+
+// fp32 operand -> hi / lo bf16 planes, with the operand's fused transform (pre-activation / activation-derivative mask)
+__global__ void split_planes_kernel(Side s, long long n8, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const bool has_aux = s.mode >= SIDE_DLRELU;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(s.p) + 2 * i), v1 = __ldg(reinterpret_cast<const float4*>(s.p) + 2 * i + 1);
+    float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    if (has_aux) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(s.aux) + 2 * i), a1 = __ldg(reinterpret_cast<const float4*>(s.aux) + 2 * i + 1);
+      const float ax[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = side_apply(x[e], ax[e], s.mode, s.slope);
+    } else if (s.mode == SIDE_LRELU) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = x[e] > 0.f ? x[e] : x[e] * s.slope;
+    }
+    uint4 h, l;
+    split8(x, h, l);
+    reinterpret_cast<uint4*>(hi)[i] = h;
+    reinterpret_cast<uint4*>(lo)[i] = l;
+  }
+}
+
+__global__ void __launch_bounds__(kWgTmaThreads, 1) wgrad_tma_kernel(const __grid_constant__ WgTcParams p, const __grid_constant__ WgTmaExtra x) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int img_a = x.rows_a_p * 128;          // one plane of one A image
+  const int img_b = x.Rp * 128;                // one plane of one B image
+  const int stage_bytes = 2 * (p.a_groups * img_a + p.b_groups * img_b);
+  uint8_t* stage0 = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)x.nstages * stage_bytes);
+  uint64_t* full = bars;                        // [nstages] TMA -> MMA
+  uint64_t* empty = bars + kWgTmaMaxStages;     // [nstages] MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * kWgTmaMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgTmaMaxStages + 1);
+  uint32_t* s_unit = tmem_slot + 2;             // [kWgMaxUnits]
+  uint8_t* ones_img = reinterpret_cast<uint8_t*>(bars) + 128;   // (Rp + 8) rows x 128 B of bf16 1.0 (only when bias_grp >= 0)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cb_tile = blockIdx.x % p.n_cb_tiles;
+  const int ca_tile = (blockIdx.x / p.n_cb_tiles) % p.n_ca_tiles;
+  const int cgrp = blockIdx.x / (p.n_cb_tiles * p.n_ca_tiles);
+  const int grp = blockIdx.y;
+  const int u0 = p.grp_first_unit[grp];
+  const int nu = p.grp_first_unit[grp + 1] - u0;
+  const int qlo = p.grp_qlo[grp];
+  const int split = blockIdx.z;
+  const bool has_bias = p.bias_grp == (int)blockIdx.y && ca_tile == 0;
+  const long long units = (long long)p.batch * x.chunks_per_batch;
+  const long long c_begin = units * split / p.nsplit;
+  const long long c_end = units * (split + 1) / p.nsplit;
+
+  if (tid == 0) {
+    for (int s = 0; s < x.nstages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
+  {  // padding rows of every image (never written by the TMA boxes): zero, so that a partial last K slice contributes nothing
+    const int a_box_rows = x.a_box_t * p.nsub;
+    const int n_img = 2 * (p.a_groups + p.b_groups);
+    for (int s = 0; s < x.nstages; ++s)
+      for (int i = 0; i < n_img; ++i) {
+        const bool is_a = i < 2 * p.a_groups;
+        uint8_t* img = stage0 + (size_t)s * stage_bytes + (is_a ? (size_t)i * img_a : (size_t)2 * p.a_groups * img_a + (size_t)(i - 2 * p.a_groups) * img_b);
+        const int r0 = is_a ? a_box_rows : x.R, r1 = is_a ? x.rows_a_p : x.Rp;
+        for (int o = r0 * 128 + tid * 16; o < r1 * 128; o += kWgTmaThreads * 16) *reinterpret_cast<uint4*>(img + o) = make_uint4(0u, 0u, 0u, 0u);
+      }
+  }
+  if (has_bias)
+    for (int i = tid; i < (x.Rp + 8) * 128 / 16; i += kWgTmaThreads) reinterpret_cast<uint4*>(ones_img)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+  if (tid >= 160 && tid < 160 + nu) {
+    const int u = tid - 160;
+    const int n_a = p.unit_tap0[u0 + u];
+    uint32_t lbo_a;
+    if (p.mode == 0) lbo_a = 2u * (uint32_t)img_a;
+    else lbo_a = p.unit_ntaps[u0 + u] == 2 ? (uint32_t)((p.tap_q[n_a + 1] - p.tap_q[n_a]) * p.nsub) * 128u : 128u;
+    const uint32_t shift = (uint32_t)((p.tap_q[n_a] - qlo) * p.nsub) * 128u;
+    s_unit[u] = (shift >> 4) + ((lbo_a >> 4) << 16);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      const uint32_t tx = 2u * (uint32_t)(p.a_groups * x.a_box_t * p.nsub + p.b_groups * x.R) * 128u;
+      const CUtensorMap* ma = &x.map_a[p.grp_rho[grp]];
+      const int ca0 = cgrp * p.ca_g + ca_tile * (p.mode == 0 ? 128 : 64);
+      const int cb0 = cgrp * p.cb_g + cb_tile * p.NT;
+      int it = 0;
+      for (long long c = c_begin; c < c_end; ++c, ++it) {
+        const int s = it % x.nstages;
+        mbar_wait(&empty[s], ((it / x.nstages) & 1) ^ 1);
+        const int bb = (int)(c / x.chunks_per_batch);
+        const int m0 = (int)(c % x.chunks_per_batch) * x.tt;
+        uint8_t* st = stage0 + (size_t)s * stage_bytes;
+        mbar_arrive_expect_tx(&full[s], tx);
+        for (int g = 0; g < p.a_groups; ++g)
+          for (int pl = 0; pl < 2; ++pl)
+            tma_load_5d(st + (size_t)(2 * g + pl) * img_a, ma, ca0 + g * 64, 0, m0 + qlo, bb, pl, &full[s]);
+        uint8_t* bst = st + (size_t)p.a_groups * 2 * img_a;
+        for (int g = 0; g < p.b_groups; ++g)
+          for (int pl = 0; pl < 2; ++pl)
+            tma_load_5d(bst + (size_t)(2 * g + pl) * img_b, &x.map_b, cb0 + g * 64, 0, m0, bb, pl, &full[s]);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, p.NT, 1, 1);
+      const uint32_t lbo_b16 = ((2u * (uint32_t)img_b) >> 4) << 16;
+      const uint32_t img_a16 = (uint32_t)img_a >> 4, img_b16 = (uint32_t)img_b >> 4;
+      const uint32_t st0_16 = smem_u32(stage0) >> 4, stage16 = (uint32_t)stage_bytes >> 4;
+      const uint32_t boff16 = (uint32_t)(p.a_groups * 2 * img_a) >> 4;
+      const uint32_t ones16 = (smem_u32(ones_img) >> 4) | ((128u >> 4) << 16);
+      const int kslices = x.Rp >> 4;
+      int it = 0;
+      for (long long c = c_begin; c < c_end; ++c, ++it) {
+        const int s = it % x.nstages;
+        mbar_wait(&full[s], (it / x.nstages) & 1);
+        tc_fence_after();
+        const uint32_t sbase = st0_16 + (uint32_t)s * stage16;
+        const uint32_t b_hi = (sbase + boff16) | lbo_b16;
+        uint32_t ua = s_unit[0];
+        for (int u = 0; u < nu; ++u) {
+          const uint32_t a_hi = sbase + ua;
+          if (u + 1 < nu) ua = s_unit[u + 1];
+          const uint32_t d = tmem_acc + (uint32_t)(u * p.NT);
+#pragma unroll 1
+          for (int ks = 0; ks < kslices; ++ks) {
+            const uint32_t ko = (uint32_t)ks * 128u;            // 16 rows x 128 bytes, in 16-byte units
+            const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+            umma_bf16_lo(d, a_hi + img_a16 + ko, b_hi + ko, idesc, acc);
+            umma_bf16_lo(d, a_hi + ko, b_hi + img_b16 + ko, idesc, 1u);
+            umma_bf16_lo(d, a_hi + ko, b_hi + ko, idesc, 1u);
+          }
+        }
+        if (has_bias) {
+          const uint32_t d = tmem_acc + (uint32_t)(nu * p.NT);
+#pragma unroll 1
+          for (int ks = 0; ks < kslices; ++ks) {
+            const uint32_t ko = (uint32_t)ks * 128u;
+            umma_bf16_lo(d, ones16 + ko, b_hi + ko, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+            umma_bf16_lo(d, ones16 + ko, b_hi + img_b16 + ko, idesc, 1u);
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+    __syncwarp();
+  } else {
+    wg_epilogue(p, tmem_full, tmem_acc, warp, lane, cb_tile, ca_tile, cgrp, u0, nu, split, has_bias);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
+  }
+}
+
 // sums the split-K partials: ws = [nsplit][stride] with stride >= n + nb; elements [0, n) -> dw, [bias_off, bias_off + nb) -> dbias
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n, int nsplit, long long stride,
                                     float* __restrict__ dbias, long long bias_off, int nb) {
@@ -316,8 +511,20 @@ struct WgPlan {
   bool ok;
   WgTcParams p;
   size_t smem;
-  long long ws_floats;
+  long long ws_floats;       // whole workspace: split-K partials (+ the bf16 operand planes of the TMA variant)
+  // TMA variant (tma == true): x, its shared-memory size, offsets (floats) of the operand planes inside the workspace
+  bool tma;
+  WgTmaExtra x;
+  size_t smem_tma;
+  long long part_floats, planes_a_off, planes_b_off;
+  int nsplit_tma;
+  int max_span_q;
 };
+
+static bool wg_want_tma() {
+  static const bool on = [] { const char* e = std::getenv("KANTTS_B200_WG_TMA"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 static WgPlan make_plan(const KtConv1dDesc* d) {
   WgPlan pl{};
@@ -381,6 +588,7 @@ static WgPlan make_plan(const KtConv1dDesc* d) {
         ++nunit;
       }
       max_span = std::max(max_span, (qhi - p.grp_qlo[g]) * p.nsub);
+      pl.max_span_q = std::max(pl.max_span_q, qhi - p.grp_qlo[g]);
     }
   }
   p.grp_first_unit[p.ngroups] = nunit;
@@ -419,6 +627,53 @@ static WgPlan make_plan(const KtConv1dDesc* d) {
   p.split_stride = n_main + (p.bias_grp >= 0 ? ((cb + 3) & ~3) : 0);
   pl.ws_floats = nsplit * p.split_stride;
   pl.ok = true;
+
+  // ---- TMA variant: chunk = tt base time steps x nsub sub-sequences, padded to whole K = 16 slices
+  pl.tma = false;
+  // (box start coordinates are multiples of the (super-)group widths: with SWIZZLE_128B they must be 16-byte aligned)
+  if (!tr && p.up == 1 && (ca % 8) == 0 && (cb % 8) == 0 && (p.ca_g % 8) == 0 && (p.cb_g % 8) == 0 && p.step <= 8 && wg_want_tma() &&
+      encode_tiled_fn() != nullptr) {
+    WgTmaExtra& x = pl.x;
+    for (int r = 0; r < p.step; ++r)
+      if (p.t_a - r <= 0) return pl;
+    // tt: rows R = tt * nsub near 64, preferring little padding in the last K slice
+    int best_tt = 0; double best_score = -1.0;
+    for (int tt = std::max(1, 40 / p.nsub); tt * p.nsub <= 96 || tt == std::max(1, 40 / p.nsub); ++tt) {
+      const int R = tt * p.nsub, Rp = (R + 15) & ~15;
+      if (tt + pl.max_span_q > 256 || R > 256) break;
+      const double score = (double)R / Rp - 0.002 * std::abs(R - 64);
+      if (score > best_score) { best_score = score; best_tt = tt; }
+    }
+    if (best_tt == 0) return pl;
+    for (int tt = best_tt; tt >= 1; tt = tt > 1 ? tt / 2 : 0) {
+      x.tt = tt; x.R = tt * p.nsub; x.Rp = (x.R + 15) & ~15;
+      x.a_box_t = tt + pl.max_span_q;
+      x.rows_a_p = (x.Rp + pl.max_span_q * p.nsub + 7) & ~7;
+      const size_t stage = 2 * ((size_t)p.a_groups * x.rows_a_p * 128 + (size_t)p.b_groups * x.Rp * 128);
+      const size_t fixed = 1024 + 128 + (p.bias_grp >= 0 ? (size_t)(x.Rp + 8) * 128 : 0);
+      const int ns = (int)std::min<size_t>(kWgTmaMaxStages, ((size_t)kMaxDynSmem - fixed) / stage);
+      if (ns >= 2) { x.nstages = ns; pl.smem_tma = fixed + ns * stage; pl.tma = true; break; }
+      if (tt == 1) break;
+    }
+    if (pl.tma) {
+      x.chunks_per_batch = ceil_div(p.M, x.tt);
+      const long long units_t = (long long)p.batch * x.chunks_per_batch;
+      long long ns_best = 1;
+      double cbest = 1e30;
+      for (long long ns = 1; ns <= std::min<long long>(units_t, 296); ++ns) {
+        const long long waves = (base * ns + 147) / 148;
+        const double cost = (double)waves * (double)((units_t + ns - 1) / ns) + (double)ns * out_chunks * 4.0;   // a chunk ~ 2.5 us here
+        if (cost < cbest - 1e-9) { cbest = cost; ns_best = ns; }
+      }
+      pl.nsplit_tma = (int)ns_best;
+      pl.part_floats = (ns_best * p.split_stride + 63) & ~63LL;
+      const long long fa = ((long long)p.batch * p.t_a * p.nsub * ca + 63) & ~63LL;     // floats = 2 planes x bf16
+      const long long fb = ((long long)p.batch * p.t_b * p.nsub * cb + 63) & ~63LL;
+      pl.planes_a_off = pl.part_floats;
+      pl.planes_b_off = pl.part_floats + fa;
+      pl.ws_floats = pl.part_floats + fa + fb;
+    }
+  }
   return pl;
 }
 
@@ -448,6 +703,43 @@ int conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy,
   if (d->transposed) { p.a = sdy; p.b = sx; }
   else { p.a = sx; p.b = sdy; }
   p.ws = ws;
+  if (pl.tma) {
+    WgTmaExtra& x = pl.x;
+    p.nsplit = pl.nsplit_tma;
+    __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(ws + pl.planes_a_off);
+    __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(ws + pl.planes_b_off);
+    const long long na = (long long)p.batch * p.t_a * p.nsub * p.ca, nb = (long long)p.batch * p.t_b * p.nsub * p.cb;
+    auto blocks_for = [](long long n8) { return (int)std::max<long long>(1, std::min<long long>((n8 + 255) / 256, 148LL * 16)); };
+    split_planes_kernel<<<blocks_for(na / 8), 256, 0, st>>>(p.a, na / 8, pa, pa + na);
+    split_planes_kernel<<<blocks_for(nb / 8), 256, 0, st>>>(p.b, nb / 8, pb, pb + nb);
+    KT_CHECK_CUDA(cudaGetLastError());
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    {
+      const cuuint64_t gdim[5] = {(cuuint64_t)p.cb, (cuuint64_t)p.nsub, (cuuint64_t)p.t_b, (cuuint64_t)p.batch, 2};
+      const cuuint64_t gstr[4] = {(cuuint64_t)p.cb * 2, (cuuint64_t)p.nsub * p.cb * 2, (cuuint64_t)p.t_b * p.nsub * p.cb * 2, (cuuint64_t)nb * 2};
+      const cuuint32_t box[5] = {64, (cuuint32_t)p.nsub, (cuuint32_t)x.tt, 1, 1};
+      const CUresult r = encode_tiled_fn()(&x.map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, pb, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      KT_REQUIRE(r == CUDA_SUCCESS, "conv1d_bwd_weight_tc: cuTensorMapEncodeTiled(B) failed (%d)", (int)r);
+    }
+    for (int rho = 0; rho < p.step; ++rho) {
+      const cuuint64_t gdim[5] = {(cuuint64_t)p.ca, (cuuint64_t)p.nsub, (cuuint64_t)ceil_div(p.t_a - rho, p.step), (cuuint64_t)p.batch, 2};
+      const cuuint64_t gstr[4] = {(cuuint64_t)p.ca * 2, (cuuint64_t)p.step * p.nsub * p.ca * 2, (cuuint64_t)p.t_a * p.nsub * p.ca * 2, (cuuint64_t)na * 2};
+      const cuuint32_t box[5] = {64, (cuuint32_t)p.nsub, (cuuint32_t)x.a_box_t, 1, 1};
+      const CUresult r = encode_tiled_fn()(&x.map_a[rho], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, pa + (long long)rho * p.nsub * p.ca, gdim, gstr, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      KT_REQUIRE(r == CUDA_SUCCESS, "conv1d_bwd_weight_tc: cuTensorMapEncodeTiled(A, residue %d) failed (%d)", rho, (int)r);
+    }
+    static std::atomic<bool> cfg_t{false};
+    if (!cfg_t.load(std::memory_order_acquire)) {
+      KT_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+      cfg_t.store(true, std::memory_order_release);
+    }
+    dim3 grid(p.groups * p.n_ca_tiles * p.n_cb_tiles, p.ngroups, p.nsplit);
+    wgrad_tma_kernel<<<grid, kWgTmaThreads, pl.smem_tma, st>>>(p, x);
+    KT_CHECK_CUDA(cudaGetLastError());
+  } else {
   static std::atomic<bool> cfg{false};
   if (!cfg.load(std::memory_order_acquire)) {
     KT_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
@@ -456,6 +748,7 @@ int conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy,
   dim3 grid(p.groups * p.n_ca_tiles * p.n_cb_tiles, p.ngroups, p.nsplit);
   wgrad_tc_kernel<<<grid, kWgThreads, pl.smem, st>>>(p);
   KT_CHECK_CUDA(cudaGetLastError());
+  }
   const long long n = (long long)p.taps_total * p.ca_g0 * p.cb;
   const int blocks = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, 148LL * 8));
   const bool fused_bias = dbias != nullptr && p.bias_grp >= 0;
