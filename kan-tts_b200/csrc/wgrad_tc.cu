@@ -504,6 +504,42 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
   }
 }
 
+// Many splits of a small gradient (thin layers: 147 splits of 7 K floats): one WARP per output float4, lanes stride over the splits
+// and combine with shuffles -- the kernel above walks the splits serially per thread (47 us for that shape with 7 CTAs).
+__global__ void wgrad_reduce_wide_kernel(const float* __restrict__ ws, float* __restrict__ dw, long long n, int nsplit, long long stride,
+                                         float* __restrict__ dbias, long long bias_off, int nb) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const bool vec = ((n | stride) & 3) == 0;
+  const long long items = vec ? n / 4 : n;
+  const long long items_b = dbias ? nb : 0;
+  for (long long i = warp; i < items + items_b; i += nwarps) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < items) {
+      if (vec) {
+        for (int s = lane; s < nsplit; s += 32) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(ws + (long long)s * stride) + i);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      } else {
+        for (int s = lane; s < nsplit; s += 32) acc.x += ws[(long long)s * stride + i];
+      }
+    } else {
+      for (int s = lane; s < nsplit; s += 32) acc.x += ws[(long long)s * stride + bias_off + (i - items)];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+      acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+    }
+    if (lane == 0) {
+      if (i >= items) dbias[i - items] = acc.x;
+      else if (vec) reinterpret_cast<float4*>(dw)[i] = acc;
+      else dw[i] = acc.x;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------
@@ -526,7 +562,7 @@ static bool wg_want_tma() {
   return on;
 }
 
-static WgPlan make_plan(const KtConv1dDesc* d) {
+static WgPlan make_plan(const KtConv1dDesc* d, bool allow_tma = true) {
   WgPlan pl{};
   pl.ok = false;
   WgTcParams& p = pl.p;
@@ -548,7 +584,14 @@ static WgPlan make_plan(const KtConv1dDesc* d) {
   if (p.step > 8) return pl;
   // channels are zero-padded to 64-wide images: thin / grouped layers use the same kernel
   p.mode = p.ca_g <= 64 ? 1 : 0;
-  p.NT = std::min(256, (p.cb_g + 63) & ~63);
+  // TMA variant (see wgrad_tma_kernel): plain convs whose box coordinates (multiples of the (super-)group widths) are 16-byte
+  // aligned.  Its tiles are N = 128 wide: a stage is then ~70 KB and the ring holds three -- the N = 256 tiles of the
+  // register-staged kernel leave room for two 100 KB stages only, and the loads of one chunk (~3 us of L2 latency +
+  // transfer) could not hide behind the 1.6 us of MMAs of the other (measured 260 cycles per N = 256 MMA against 77 per
+  // N = 128 MMA with three stages, call r2ab).
+  const bool tma_ok = allow_tma && !tr && p.up == 1 && (ca % 8) == 0 && (cb % 8) == 0 && (p.ca_g % 8) == 0 && (p.cb_g % 8) == 0 &&
+                      wg_want_tma() && encode_tiled_fn() != nullptr;
+  p.NT = std::min(tma_ok ? 128 : 256, (p.cb_g + 63) & ~63);
   p.n_cb_tiles = ceil_div(p.cb_g, p.NT);
   p.n_ca_tiles = p.mode == 0 ? ceil_div(p.ca_g, 128) : 1;
   p.a_groups = p.mode == 0 ? 2 : 1;
@@ -630,49 +673,52 @@ static WgPlan make_plan(const KtConv1dDesc* d) {
 
   // ---- TMA variant: chunk = tt base time steps x nsub sub-sequences, padded to whole K = 16 slices
   pl.tma = false;
-  // (box start coordinates are multiples of the (super-)group widths: with SWIZZLE_128B they must be 16-byte aligned)
-  if (!tr && p.up == 1 && (ca % 8) == 0 && (cb % 8) == 0 && (p.ca_g % 8) == 0 && (p.cb_g % 8) == 0 && p.step <= 8 && wg_want_tma() &&
-      encode_tiled_fn() != nullptr) {
+  if (tma_ok) {
     WgTmaExtra& x = pl.x;
     for (int r = 0; r < p.step; ++r)
-      if (p.t_a - r <= 0) return pl;
-    // tt: rows R = tt * nsub near 64, preferring little padding in the last K slice
-    int best_tt = 0; double best_score = -1.0;
-    for (int tt = std::max(1, 40 / p.nsub); tt * p.nsub <= 96 || tt == std::max(1, 40 / p.nsub); ++tt) {
+      if (p.t_a - r <= 0) return make_plan(d, false);
+    // tt: the largest chunk (R = tt * nsub <= 128 rows, at most 20 % padding in the last K slice) that still leaves a ring of
+    // three stages; else the deepest ring
+    int best_tt = 0, best_ns = 0;
+    for (int tt = std::max(1, 128 / p.nsub); tt >= 1; --tt) {
       const int R = tt * p.nsub, Rp = (R + 15) & ~15;
-      if (tt + pl.max_span_q > 256 || R > 256) break;
-      const double score = (double)R / Rp - 0.002 * std::abs(R - 64);
-      if (score > best_score) { best_score = score; best_tt = tt; }
-    }
-    if (best_tt == 0) return pl;
-    for (int tt = best_tt; tt >= 1; tt = tt > 1 ? tt / 2 : 0) {
-      x.tt = tt; x.R = tt * p.nsub; x.Rp = (x.R + 15) & ~15;
-      x.a_box_t = tt + pl.max_span_q;
-      x.rows_a_p = (x.Rp + pl.max_span_q * p.nsub + 7) & ~7;
-      const size_t stage = 2 * ((size_t)p.a_groups * x.rows_a_p * 128 + (size_t)p.b_groups * x.Rp * 128);
-      const size_t fixed = 1024 + 128 + (p.bias_grp >= 0 ? (size_t)(x.Rp + 8) * 128 : 0);
+      if (tt + pl.max_span_q > 256 || R > 256 || (tt > 1 && R * 5 < Rp * 4)) continue;
+      const int rows_a_p = (Rp + pl.max_span_q * p.nsub + 7) & ~7;
+      const size_t stage = 2 * ((size_t)p.a_groups * rows_a_p * 128 + (size_t)p.b_groups * Rp * 128);
+      const size_t fixed = 1024 + 128 + (p.bias_grp >= 0 ? (size_t)(Rp + 8) * 128 : 0);
+      if (fixed + stage > (size_t)kMaxDynSmem) continue;
       const int ns = (int)std::min<size_t>(kWgTmaMaxStages, ((size_t)kMaxDynSmem - fixed) / stage);
-      if (ns >= 2) { x.nstages = ns; pl.smem_tma = fixed + ns * stage; pl.tma = true; break; }
-      if (tt == 1) break;
+      if (ns > best_ns) { best_ns = ns; best_tt = tt; }
+      if (ns >= 3) break;
     }
-    if (pl.tma) {
-      x.chunks_per_batch = ceil_div(p.M, x.tt);
-      const long long units_t = (long long)p.batch * x.chunks_per_batch;
-      long long ns_best = 1;
-      double cbest = 1e30;
-      for (long long ns = 1; ns <= std::min<long long>(units_t, 296); ++ns) {
-        const long long waves = (base * ns + 147) / 148;
-        const double cost = (double)waves * (double)((units_t + ns - 1) / ns) + (double)ns * out_chunks * 4.0;   // a chunk ~ 2.5 us here
-        if (cost < cbest - 1e-9) { cbest = cost; ns_best = ns; }
-      }
-      pl.nsplit_tma = (int)ns_best;
-      pl.part_floats = (ns_best * p.split_stride + 63) & ~63LL;
-      const long long fa = ((long long)p.batch * p.t_a * p.nsub * ca + 63) & ~63LL;     // floats = 2 planes x bf16
-      const long long fb = ((long long)p.batch * p.t_b * p.nsub * cb + 63) & ~63LL;
-      pl.planes_a_off = pl.part_floats;
-      pl.planes_b_off = pl.part_floats + fa;
-      pl.ws_floats = pl.part_floats + fa + fb;
+    if (best_ns < 2) return make_plan(d, false);
+    x.tt = best_tt; x.R = best_tt * p.nsub; x.Rp = (x.R + 15) & ~15;
+    x.a_box_t = best_tt + pl.max_span_q;
+    x.rows_a_p = (x.Rp + pl.max_span_q * p.nsub + 7) & ~7;
+    x.nstages = best_ns;
+    {
+      const size_t stage = 2 * ((size_t)p.a_groups * x.rows_a_p * 128 + (size_t)p.b_groups * x.Rp * 128);
+      pl.smem_tma = 1024 + 128 + (p.bias_grp >= 0 ? (size_t)(x.Rp + 8) * 128 : 0) + (size_t)best_ns * stage;
     }
+    pl.tma = true;
+    x.chunks_per_batch = ceil_div(p.M, x.tt);
+    const long long units_t = (long long)p.batch * x.chunks_per_batch;
+    // split-K: a chunk costs ~2 us here (TMA + MMAs), one more partial copy of the gradient out_bytes / ~4 TB/s twice
+    const double out_cost = (double)p.taps_total * p.ca_g0 * cb * 8.0 / 4e12 / 2e-6;
+    long long ns_best = 1;
+    double cbest = 1e30;
+    for (long long ns = 1; ns <= std::min<long long>(units_t, 296); ++ns) {
+      const long long waves = (base * ns + 147) / 148;
+      const double cost = (double)waves * (double)((units_t + ns - 1) / ns) + (double)ns * out_cost;
+      if (cost < cbest - 1e-9) { cbest = cost; ns_best = ns; }
+    }
+    pl.nsplit_tma = (int)ns_best;
+    pl.part_floats = (ns_best * p.split_stride + 63) & ~63LL;
+    const long long fa = ((long long)p.batch * p.t_a * p.nsub * ca + 63) & ~63LL;     // floats = 2 planes x bf16
+    const long long fb = ((long long)p.batch * p.t_b * p.nsub * cb + 63) & ~63LL;
+    pl.planes_a_off = pl.part_floats;
+    pl.planes_b_off = pl.part_floats + fa;
+    pl.ws_floats = pl.part_floats + fa + fb;
   }
   return pl;
 }
@@ -752,7 +798,13 @@ int conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy,
   const long long n = (long long)p.taps_total * p.ca_g0 * p.cb;
   const int blocks = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, 148LL * 8));
   const bool fused_bias = dbias != nullptr && p.bias_grp >= 0;
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dw, n, p.nsplit, p.split_stride, fused_bias ? dbias : nullptr, p.bias_off, d->c_out);
+  if (p.nsplit >= 16) {
+    const long long warps = n / 4 + d->c_out;
+    const int wblocks = (int)std::max<long long>(1, std::min<long long>((warps + 7) / 8, 148LL * 8));
+    wgrad_reduce_wide_kernel<<<wblocks, 256, 0, st>>>(ws, dw, n, p.nsplit, p.split_stride, fused_bias ? dbias : nullptr, p.bias_off, d->c_out);
+  } else {
+    wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(ws, dw, n, p.nsplit, p.split_stride, fused_bias ? dbias : nullptr, p.bias_off, d->c_out);
+  }
   KT_CHECK_CUDA(cudaGetLastError());
   if (dbias && !fused_bias) {
     const long long rows = (long long)d->batch * d->nsub * d->t_out;
