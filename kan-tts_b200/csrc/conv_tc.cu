@@ -22,6 +22,7 @@
 //              residual (or act' mask for the data gradient), 16-byte stores to the channels-last output.
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -283,6 +284,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         trace_ev(p, 2, ti, 1);
         const uint32_t d_tmem = tmem_acc + (uint32_t)buf * buf_cols;
         uint32_t acc = 0;
+        const bool tr_on = p.trace != nullptr && blockIdx.x == 0 && ti < kTraceTiles;   // role 6: cycles this tile's issuer waited
+        long long w_a = 0, w_b = 0, t_w = 0;
         int ph = 0;
         while ((tile % mtiles) >= p.ph_mt0[ph + 1]) ++ph;
         const int g_begin = p.ph_g0[ph], g_end = p.ph_g0[ph + 1];
@@ -292,7 +295,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
             const int sa = it_a % p.na_stages;
             // (no tcgen05.fence here or after the weight wait: the producers' fence.proxy.async + mbarrier release
             //  / the bulk copy's complete_tx make the data visible to the MMA's async-proxy reads)
+            if (tr_on) t_w = clock64();
             mbar_wait(&full_a[sa], (it_a / p.na_stages) & 1);
+            if (tr_on) w_a += clock64() - t_w;
             if (c == 0 && g == g_begin) trace_ev(p, 2, ti, 2);
             const uint32_t a16 = a_base16 + (uint32_t)sa * a_stage16;
             const int n_begin = p.grp_first[g], n_end = p.grp_first[g + 1];
@@ -306,7 +311,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
                 if (ti == 0) mbar_wait(&full_b[sb], 0u);
               } else {
                 sb = it_b % p.nb_stages;
+                if (tr_on) t_w = clock64();
                 mbar_wait(&full_b[sb], (uint32_t)((it_b / p.nb_stages) & 1));
+                if (tr_on) w_b += clock64() - t_w;
               }
               const uint32_t b_hi = b_base16 + (uint32_t)sb * b_stage16;
               if (p.dbg & 64) {
@@ -338,6 +345,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         }
         umma_commit(&tmem_full[buf]);
         trace_ev(p, 2, ti, 3);
+        if (tr_on) {
+          long long* t6 = p.trace + (6 * kTraceTiles + ti) * kTraceEvents;
+          t6[0] = w_a; t6[1] = w_b; t6[2] = it_b; t6[3] = p.na_stages * 100 + p.nb_stages;
+        }
       }
     }
     __syncwarp();
@@ -718,6 +729,11 @@ static int g_dbg = 0;
 void debug_set_flags(int f) { g_dbg = f; }
 void debug_set_trace(long long* dev_buf) { g_trace = dev_buf; }
 
+static bool tc_env_flag(const char* name) {
+  const char* e = std::getenv(name);
+  return e && e[0] == '1';
+}
+
 static int run_tc(TcParams p, cudaStream_t st) {   // p: phases already planned by plan_launches
   p.trace = g_trace;
   p.dbg = g_dbg;
@@ -736,7 +752,13 @@ static int run_tc(TcParams p, cudaStream_t st) {   // p: phases already planned 
     p.nb_stages = slots;
     p.na_stages = (budget - slots * b_stage) / a_stage >= 3 ? 3 : 2;
   } else {
-    p.na_stages = 3;
+    // The weight ring is what bounds wide layers: a stage (32 KB at N = 128) arrives ~0.65 us after its copy is issued, so a
+    // ring of two stages paces every (tap, chunk) step at ~0.65 us against 0.4 us of MMAs (call r2y: removing the MMAs, the
+    // producers or the copies one at a time changed nothing).  Layers with >= 4 taps per activation image spend long enough
+    // on one image for its successor to be staged meanwhile: they give the third image stage to the weight ring.
+    int min_taps = kMaxTaps;
+    for (int g = 0; g < p.ngroups; ++g) min_taps = std::min(min_taps, p.grp_first[g + 1] - p.grp_first[g]);
+    p.na_stages = (min_taps >= 4 && !tc_env_flag("KANTTS_B200_TC_NA3")) ? 2 : 3;
     if (3 * a_stage + 3 * b_stage > budget) p.na_stages = 2;
     p.nb_stages = std::min(6, (budget - p.na_stages * a_stage) / b_stage);
   }

@@ -63,6 +63,7 @@ struct WgTcParams {
   // goes to the split's slice of the workspace at `bias_off` and wgrad_reduce sums the splits like any other element
   int bias_grp;
   long long bias_off, split_stride;
+  float* bias_direct;   // nsplit == 1: the kernel writes dw / dbias itself (ws = dw, no reduce pass); else nullptr
 };
 
 // TMEM -> workspace partial tiles (warps 0-3 of either kernel; thread = accumulator row)
@@ -116,7 +117,8 @@ __device__ __forceinline__ void wg_epilogue(const WgTcParams& p, uint64_t* tmem_
     if (has_bias && warp == 0) {   // accumulator unit `nu`: every row = column sums; row 0 (lane 0) stores them
       const int col0 = cb_tile * p.NT;
       const int ncol = min(p.NT, p.cb_g - col0);
-      float* dst = p.ws + (long long)split * p.split_stride + p.bias_off + (long long)cgrp * p.cb_g + col0;
+      float* dst = p.bias_direct ? p.bias_direct + (long long)cgrp * p.cb_g + col0
+                                 : p.ws + (long long)split * p.split_stride + p.bias_off + (long long)cgrp * p.cb_g + col0;
       for (int n0 = 0; n0 < p.NT; n0 += 32) {
         uint32_t rr[32];
         tmem_ld32(tmem_acc + (uint32_t)(nu * p.NT + n0), rr);
@@ -440,13 +442,17 @@ __global__ void __launch_bounds__(kWgTmaThreads, 1) wgrad_tma_kernel(const __gri
           const uint32_t a_hi = sbase + ua;
           if (u + 1 < nu) ua = s_unit[u + 1];
           const uint32_t d = tmem_acc + (uint32_t)(u * p.NT);
-#pragma unroll 1
-          for (int ks = 0; ks < kslices; ++ks) {
-            const uint32_t ko = (uint32_t)ks * 128u;            // 16 rows x 128 bytes, in 16-byte units
-            const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
-            umma_bf16_lo(d, a_hi + img_a16 + ko, b_hi + ko, idesc, acc);
-            umma_bf16_lo(d, a_hi + ko, b_hi + img_b16 + ko, idesc, 1u);
-            umma_bf16_lo(d, a_hi + ko, b_hi + ko, idesc, 1u);
+          // (fully unrolled with a uniform predicate per slice: the rolled loop re-materialised its loop-invariant descriptor
+          //  words every iteration -- 2 R2UR + 4 ULEA + 4 UMOV per 3 UTCHMMA, ~97 cycles per MMA measured on N = 64 tiles)
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            if (ks < kslices) {
+              const uint32_t ko = (uint32_t)ks * 128u;            // 16 rows x 128 bytes, in 16-byte units
+              const uint32_t acc = (it > 0 || ks > 0) ? 1u : 0u;
+              umma_bf16_lo(d, a_hi + img_a16 + ko, b_hi + ko, idesc, acc);
+              umma_bf16_lo(d, a_hi + ko, b_hi + img_b16 + ko, idesc, 1u);
+              umma_bf16_lo(d, a_hi + ko, b_hi + ko, idesc, 1u);
+            }
           }
         }
         if (has_bias) {
@@ -611,6 +617,11 @@ static WgPlan make_plan(const KtConv1dDesc* d, bool allow_tma = true) {
     }
     std::sort(tq.begin(), tq.end());
     size_t i = 0;
+    // the residue's units are spread EVENLY over its unit groups (5 taps, U = 4: groups of 3 + 2, not 4 + 1): every CTA loads
+    // the same operand rows per chunk whatever its unit count, so the largest group sets the pace
+    const int units_r = ceil_div((int)tq.size(), taps_per_unit);
+    const int groups_r = std::max(1, ceil_div(units_r, U));
+    const int U_r = ceil_div(units_r, groups_r);
     while (i < tq.size()) {
       // one unit group: up to U units of this residue
       if (p.ngroups >= kWgMaxGroups) return pl;
@@ -619,7 +630,7 @@ static WgPlan make_plan(const KtConv1dDesc* d, bool allow_tma = true) {
       p.grp_qlo[g] = tq[i].first;
       p.grp_first_unit[g] = nunit;
       int qhi = tq[i].first;
-      for (int u = 0; u < U && i < tq.size(); ++u) {
+      for (int u = 0; u < U_r && i < tq.size(); ++u) {
         p.unit_tap0[nunit] = ntap;
         const int nt_u = (int)std::min<size_t>(taps_per_unit, tq.size() - i);
         p.unit_ntaps[nunit] = nt_u;
@@ -704,12 +715,19 @@ static WgPlan make_plan(const KtConv1dDesc* d, bool allow_tma = true) {
     x.chunks_per_batch = ceil_div(p.M, x.tt);
     const long long units_t = (long long)p.batch * x.chunks_per_batch;
     // split-K: a chunk costs ~2 us here (TMA + MMAs), one more partial copy of the gradient out_bytes / ~4 TB/s twice
-    const double out_cost = (double)p.taps_total * p.ca_g0 * cb * 8.0 / 4e12 / 2e-6;
+    // (all in us) a chunk: the larger of its loads (~1.5 us per 70 KB at the observed ~45 GB/s per SM) and its MMAs (12 per unit
+    // and 64 rows, N / 2 cycles each); one split more: one more partial copy written and read back (~4 TB/s), and the
+    // reduce pass itself (~5 us) which a single split does not need at all (the kernel then writes dw directly)
+    int u_max = 1;
+    for (int g = 0; g < p.ngroups; ++g) u_max = std::max(u_max, p.grp_first_unit[g + 1] - p.grp_first_unit[g]);
+    const double stage_kb = 2.0 * (p.a_groups * x.rows_a_p + p.b_groups * x.Rp) * 128 / 1024.0;
+    const double chunk_us = std::max(stage_kb / 45.0, u_max * 3.0 * (x.Rp / 16) * (p.NT / 2) / 1900.0);
+    const double out_us = (double)p.taps_total * p.ca_g0 * cb * 8.0 / 4e12 * 1e6;
     long long ns_best = 1;
     double cbest = 1e30;
     for (long long ns = 1; ns <= std::min<long long>(units_t, 296); ++ns) {
       const long long waves = (base * ns + 147) / 148;
-      const double cost = (double)waves * (double)((units_t + ns - 1) / ns) + (double)ns * out_cost;
+      const double cost = (double)waves * (double)((units_t + ns - 1) / ns) * chunk_us + (ns > 1 ? 5.0 + (double)ns * out_us : 0.0);
       if (cost < cbest - 1e-9) { cbest = cost; ns_best = ns; }
     }
     pl.nsplit_tma = (int)ns_best;
@@ -749,9 +767,13 @@ int conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy,
   if (d->transposed) { p.a = sdy; p.b = sx; }
   else { p.a = sx; p.b = sdy; }
   p.ws = ws;
+  p.bias_direct = nullptr;
+  if (pl.tma) p.nsplit = pl.nsplit_tma;
+  if (dbias == nullptr) p.bias_grp = -1;
+  const bool direct = p.nsplit == 1;      // one split: the partial tile IS the gradient
+  if (direct) { p.ws = dw; p.bias_direct = dbias; }
   if (pl.tma) {
     WgTmaExtra& x = pl.x;
-    p.nsplit = pl.nsplit_tma;
     __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(ws + pl.planes_a_off);
     __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(ws + pl.planes_b_off);
     const long long na = (long long)p.batch * p.t_a * p.nsub * p.ca, nb = (long long)p.batch * p.t_b * p.nsub * p.cb;
@@ -798,7 +820,9 @@ int conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy,
   const long long n = (long long)p.taps_total * p.ca_g0 * p.cb;
   const int blocks = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, 148LL * 8));
   const bool fused_bias = dbias != nullptr && p.bias_grp >= 0;
-  if (p.nsplit >= 16) {
+  if (direct) {
+    // nothing to reduce
+  } else if (p.nsplit >= 16) {
     const long long warps = n / 4 + d->c_out;
     const int wblocks = (int)std::max<long long>(1, std::min<long long>((warps + 7) / 8, 148LL * 8));
     wgrad_reduce_wide_kernel<<<wblocks, 256, 0, st>>>(ws, dw, n, p.nsplit, p.split_stride, fused_bias ? dbias : nullptr, p.bias_off, d->c_out);

@@ -41,22 +41,22 @@ for name, (kw, B, T, period, resid) in LAYERS.items():
             y = ops.conv(x, spec, cache, v, None, bias, r)
         e1.record(); torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 100
-        tr = torch.zeros(6 * 16 * 4, dtype=torch.int64, device="cuda")
+        tr = torch.zeros(8 * 16 * 4, dtype=torch.int64, device="cuda")
         lib.kt_debug_set_trace(tr.data_ptr())
         y = ops.conv(x, spec, cache, v, None, bias, r)
         torch.cuda.synchronize()
         lib.kt_debug_set_trace(None)
-    t = tr.cpu().view(6, 16, 4)
-    t0 = int(t[t > 0].min())
+    t = tr.cpu().view(8, 16, 4)
+    t0 = int(t[:6][t[:6] > 0].min())
     rel = lambda a: "   -  " if a == 0 else f"{(a - t0) / 1.9e3:6.1f}"
     print(f"=== {name}: {us:.1f} us/launch (warm, back to back); CTA0 timeline in us (clock64 / 1.9 GHz)")
     for ti in range(10):
-        if int(t[:, ti].max()) == 0:
+        if int(t[:6, ti].max()) == 0:
             break
         row = []
         for role, nm in ((0, "P0"), (1, "P1"), (2, "MMA"), (3, "EPI")):
             row.append(nm + ":" + " ".join(rel(int(t[role, ti, e])) for e in range(4 if role >= 2 else 2)))
-        print(f"  tile {ti}: " + " | ".join(row))
+        print(f"  tile {ti}: " + " | ".join(row) + f" | issuer waited: images {int(t[6, ti, 0]) / 1.9e3:5.1f} us, weights {int(t[6, ti, 1]) / 1.9e3:5.1f} us (steps so far {int(t[6, ti, 2])}, stages a/b {int(t[6, ti, 3])})")
     for role, ttl in ((4, "tile 0"), (5, "tile 1")):
         chunks = [n for n in range(16) if int(t[role, n].max()) > 0]
         if chunks:
@@ -90,12 +90,12 @@ for name in ("gen_128_128_k11", "gen_32_32_k7", "gen_64_64_k7"):
                 y = ops.conv(x, spec, cache, v, None, bias, r)
             e1.record(); torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 100
-            tr = torch.zeros(6 * 16 * 4, dtype=torch.int64, device="cuda")
+            tr = torch.zeros(8 * 16 * 4, dtype=torch.int64, device="cuda")
             lib.kt_debug_set_trace(tr.data_ptr())
             y = ops.conv(x, spec, cache, v, None, bias, r)
             torch.cuda.synchronize()
             lib.kt_debug_set_trace(None)
-            t = tr.cpu().view(6, 16, 4)
+            t = tr.cpu().view(8, 16, 4)
             ep = [(int(t[3, ti, 3]) - int(t[3, ti, 1])) / 1.9e3 for ti in range(2)]
             mm = [(int(t[2, ti, 3]) - int(t[2, ti, 2])) / 1.9e3 for ti in range(2)]
             print(f"  {name:18s} flags {flags:2d}: {us:6.1f} us/launch | epilogue tile0 {ep[0]:5.1f} us tile1 {ep[1]:5.1f} us | MMA phase tile0 {mm[0]:5.1f} tile1 {mm[1]:5.1f}")
