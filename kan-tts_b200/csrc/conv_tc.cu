@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tma.cuh"
 
 namespace kt {
 
@@ -131,12 +132,157 @@ struct TcParams {
   // development aid (kt_debug_set_trace): CTA 0 records clock64() per role / tile / event, see scripts/tc_trace.py
   long long* trace;
   int dbg;      // development aid (kt_debug_set_flags): ablation switches for timing experiments, results are WRONG when non-zero
+  // TMA epilogue (plain single-phase layers, see epilogue_tma): output / side (residual or activation-derivative operand)
+  // tensors as 3-D maps (channels, rows of one item, items), boxes of 16 channels x 32 rows, SWIZZLE_64B
+  int epi_tma;
+  int epi_split;   // 1: both epilogue groups drain EVERY tile (half of its columns each) instead of alternate tiles
+  int epi_alias;   // 1: every CTA has at most one tile -- its epilogue boxes reuse the (then idle) operand stages
+  alignas(64) CUtensorMap map_out;
+  alignas(64) CUtensorMap map_side;
 };
+
+constexpr int kEpiBufBytes = 32 * 16 * 4;   // one 32-row x 16-column fp32 box
+constexpr int kEpiBufs = 3;                 // per epilogue warp: (side load ->) combine -> store, three boxes in rotation
 
 constexpr int kTraceTiles = 16, kTraceEvents = 4;
 __device__ __forceinline__ void trace_ev(const TcParams& p, int role, int tile_i, int ev) {
   if (p.trace != nullptr && blockIdx.x == 0 && tile_i < kTraceTiles)
     p.trace[(role * kTraceTiles + tile_i) * kTraceEvents + ev] = clock64();
+}
+
+// Epilogue through the TMA unit.  The register-path epilogue below spends ~2.7 us per 32-column chunk of a warp on a chain of
+// dependent shared / global memory instructions (transposition tile -> coalesced 16-byte stores, residual loads from
+// L2): 11 us per 128 x 128 tile, 25 us per 128 x 256 tile, fully exposed on the last (or only) tile of a CTA (in-kernel
+// timeline, call r2ae).  Here a warp writes its 32 rows x 16 columns straight from the tcgen05.ld layout (thread = row)
+// into a SWIZZLE_64B box -- the XOR the transposition tile already used, so the stores are conflict-free -- and one
+// elected lane hands the box to cp.async.bulk.tensor (store): coalescing, row clipping at the end of the item and
+// the global write itself are the TMA unit's.  A residual / derivative-mask operand is PREFETCHED into the same box two
+// boxes ahead (bulk tensor load on a per-box mbarrier) and combined in place.  Three boxes per warp rotate.
+template <bool SIMPLE>
+__device__ __forceinline__ void epilogue_tma(const TcParams& p, uint32_t tmem_acc, uint32_t buf_cols, uint64_t* tmem_full, uint64_t* tmem_empty,
+                                             uint8_t* ebuf, uint64_t* ebar, float* sbias, int quarter, int egrp, int lane, int total_tiles,
+                                             int mtiles, bool tracer) {
+  const bool split = p.epi_split != 0;
+  const int halves_tile = p.NT >> 4;                       // 16-column boxes per tile row block
+  const int h_begin = split ? egrp * (halves_tile >> 1) : 0;
+  const int h_end = split ? h_begin + (halves_tile >> 1) : halves_tile;
+  const int side_kind = p.resid ? 1 : (p.mask.p ? 2 : 0);  // 0 none, 1 residual add, 2 LeakyReLU-derivative mask
+  const uint32_t sw = (uint32_t)((lane >> 1) & 3);          // SWIZZLE_64B: 16-byte chunk index ^= address bits [7, 9) = (row >> 1) & 3
+  uint32_t k = 0;                                           // boxes this warp has handled so far (buffer rotation / barrier phases)
+  int ti = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    if (!split && (ti & 1) != egrp) continue;
+    const int mt = tile % mtiles, nt = (tile / mtiles) % p.ntiles, bb = tile / (mtiles * p.ntiles);
+    const int buf = ti & 1;
+    const int r0 = mt * kTcM + quarter * 32;               // this warp's first row inside the item (flattened (time, sub-sequence))
+    const int c_tile = nt * p.n_stride;
+    const int n_valid = min(p.n_stride, p.c_out - c_tile);
+    if (tracer) trace_ev(p, 3, ti, 0);
+    if (side_kind && lane == 0) {   // side boxes of the first two column blocks (their buffers: last read by stores k-3 and k-2)
+      bulk_wait_group_read<1>();
+      for (int j = 0; j < 2; ++j)
+        if (h_begin + j < h_end) {
+          const uint32_t b = (k + j) % kEpiBufs;
+          mbar_arrive_expect_tx(&ebar[b], (uint32_t)kEpiBufBytes);
+          tma_load_3d(ebuf + b * kEpiBufBytes, &p.map_side, c_tile + (h_begin + j) * 16, r0, bb, &ebar[b]);
+        }
+    }
+    if (p.bias) {
+      __syncwarp();
+      for (int e = lane; e < p.NT; e += 32) sbias[e] = e < n_valid ? __ldg(p.bias + c_tile + e) : 0.f;
+      __syncwarp();
+    }
+    mbar_wait(&tmem_full[buf], (ti >> 1) & 1);
+    tc_fence_after();
+    if (tracer) trace_ev(p, 3, ti, 1);
+    const uint32_t t_lane = tmem_acc + (uint32_t)buf * buf_cols + ((uint32_t)(quarter * 32) << 16);
+    for (int hh = h_begin; hh < h_end; hh += 2) {
+      const int n0 = hh * 16;
+      const int nh = min(2, h_end - hh);
+      uint32_t rr[32];
+      if (nh == 2) {
+        tmem_ld32(t_lane + (uint32_t)n0, rr);
+      } else {
+        uint32_t r16[16];
+        tmem_ld16(t_lane + (uint32_t)n0, r16);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) { rr[e] = r16[e]; rr[16 + e] = 0u; }
+      }
+      tmem_ld_wait();
+      if (p.fuse2) {   // + the hi*lo products (columns [NT, 2*NT))
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (h < nh) {
+            uint32_t t2[16];
+            tmem_ld16(t_lane + (uint32_t)(p.NT + n0 + 16 * h), t2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) rr[16 * h + e] = __float_as_uint(__uint_as_float(rr[16 * h + e]) + __uint_as_float(t2[e]));
+          }
+        }
+      }
+      if (hh + 2 >= h_end) {   // last TMEM read of this warp for this tile: hand the buffer back to the MMA issuer
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[buf]);
+        if (tracer) trace_ev(p, 3, ti, 2);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h < nh) {
+          const uint32_t b = k % kEpiBufs;
+          uint8_t* box = ebuf + b * kEpiBufBytes;
+          if (side_kind) {
+            mbar_wait(&ebar[b], (k / kEpiBufs) & 1);       // the side operand of this box has landed
+          } else {
+            if (lane == 0) bulk_wait_group_read<2>();        // the store that last used this box (k - 3) has read it
+            __syncwarp();
+          }
+#pragma unroll
+          for (int e4 = 0; e4 < 4; ++e4) {
+            const int e = h * 16 + e4 * 4;
+            float v[4] = {__uint_as_float(rr[e]), __uint_as_float(rr[e + 1]), __uint_as_float(rr[e + 2]), __uint_as_float(rr[e + 3])};
+            if (p.bias) {
+              const float4 bv = *reinterpret_cast<const float4*>(sbias + n0 + e);
+              v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
+            }
+            if (p.out_act == KT_ACT_LRELU) {
+#pragma unroll
+              for (int z = 0; z < 4; ++z) v[z] = v[z] > 0.f ? v[z] : v[z] * p.out_slope;
+            } else if (!SIMPLE && p.out_act == KT_ACT_TANH) {
+#pragma unroll
+              for (int z = 0; z < 4; ++z) v[z] = tanhf(v[z]);
+            }
+            float4* cell = reinterpret_cast<float4*>(box + lane * 64 + (((uint32_t)e4 ^ sw) << 4));
+            if (side_kind == 1) {
+              const float4 a = *cell;
+              v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+            } else if (side_kind == 2) {
+              const float4 a = *cell;
+              v[0] = a.x > 0.f ? v[0] : v[0] * p.mask.slope; v[1] = a.y > 0.f ? v[1] : v[1] * p.mask.slope;
+              v[2] = a.z > 0.f ? v[2] : v[2] * p.mask.slope; v[3] = a.w > 0.f ? v[3] : v[3] * p.mask.slope;
+            }
+            *cell = make_float4(v[0], v[1], v[2], v[3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&p.map_out, box, c_tile + n0 + h * 16, r0, bb);
+            bulk_commit_group();
+            if (side_kind && hh + h + 2 < h_end) {   // side operand of the box after next -> the buffer store k-1 used
+              bulk_wait_group_read<1>();
+              const uint32_t b2 = (k + 2) % kEpiBufs;
+              mbar_arrive_expect_tx(&ebar[b2], (uint32_t)kEpiBufBytes);
+              tma_load_3d(ebuf + b2 * kEpiBufBytes, &p.map_side, c_tile + n0 + (h + 2) * 16, r0, bb, &ebar[b2]);
+            }
+          }
+          ++k;
+        }
+      }
+    }
+    if (tracer) trace_ev(p, 3, ti, 3);
+  }
+  if (lane == 0) bulk_wait_group_read<0>();   // the boxes must outlive their stores' reads
+  __syncwarp();
 }
 
 // warps 0-3 and 10-13 stage activations (two producer groups filling ALTERNATE pipeline stages, so two images'
@@ -161,7 +307,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   const int b_stage_bytes = 2 * p.NT * 128;           // hi + lo weight tile
   uint8_t* a_base = smem;
   uint8_t* b_base = a_base + (size_t)p.na_stages * a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_base + (size_t)p.nb_stages * b_stage_bytes);
+  // epilogue boxes (1024-byte aligned: the TMA path's SWIZZLE_64B pattern is a function of address bits):
+  // register path 8 warps x one 2 KB transposition tile, TMA path 8 warps x kEpiBufs boxes
+  uint8_t* s_end = b_base + (size_t)p.nb_stages * b_stage_bytes;
+  uint8_t* e_base = p.epi_alias ? a_base : s_end;
+  const int e_bytes = p.epi_alias ? 0 : (p.epi_tma ? 8 * kEpiBufs * kEpiBufBytes : 8 * 2048);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_end + e_bytes);
   uint64_t* full_a = bars;                         // [na]
   uint64_t* empty_a = full_a + p.na_stages;        // [na]
   uint64_t* full_b = empty_a + p.na_stages;        // [nb]
@@ -172,8 +323,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   // per-tap image row shift in descriptor units (16 bytes): the MMA issuer reads it with one LDS per tap instead of a
   // dynamically indexed kernel-parameter load (constant-bank miss + address arithmetic on the issuing thread)
   uint32_t* s_tapshift = tmem_slot + 4;          // [kMaxTaps]
-  float* epi_stage = reinterpret_cast<float*>(s_tapshift + kMaxTaps);   // 8 epilogue warps x (32 rows x 16 fp32), 16-byte aligned
-  float* epi_bias = epi_stage + 8 * 32 * 16;                            // 8 epilogue warps x 256 floats
+  float* epi_stage = reinterpret_cast<float*>(e_base);                  // 8 epilogue warps x (32 rows x 16 fp32)
+  float* epi_bias = reinterpret_cast<float*>(s_tapshift + kMaxTaps);    // 8 epilogue warps x 256 floats, 16-byte aligned
+  uint64_t* epi_bar = reinterpret_cast<uint64_t*>(epi_bias + 8 * 256);  // TMA path: 8 warps x kEpiBufs side-operand barriers
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int mtiles = p.ph_mt0[p.nphases];   // m-tiles of all phases (each: 128 flattened outputs m * nsub + w)
@@ -182,7 +334,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   if (tid == 0) {
     for (int s = 0; s < p.na_stages; ++s) { mbar_init(&full_a[s], 128); mbar_init(&empty_a[s], 1); }
     for (int s = 0; s < p.nb_stages; ++s) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], (p.epi_tma && p.epi_split) ? 256 : 128); }
+    if (p.epi_tma)
+      for (int s = 0; s < 8 * kEpiBufs; ++s) mbar_init(&epi_bar[s], 1);
     mbar_fence_init();
     fence_proxy_async();
   }
@@ -369,6 +523,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     float* stg = epi_stage + (size_t)ewarp * (32 * 16);
     float* sbias = epi_bias + ewarp * 256;          // this warp's copy of the tile's bias (NT <= 256 floats)
     const bool tracer = (tid == 192 || tid == 448);
+    if (p.epi_tma) {
+      epilogue_tma<SIMPLE>(p, tmem_acc, buf_cols, tmem_full, tmem_empty, e_base + (size_t)ewarp * (kEpiBufs * kEpiBufBytes),
+                           epi_bar + ewarp * kEpiBufs, sbias, quarter, egrp, lane, total_tiles, mtiles, tracer);
+    } else {
     int ti = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       if ((ti & 1) != egrp) continue;
@@ -533,6 +691,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       }
       if (tracer) trace_ev(p, 3, ti, 3);
     }
+    }
   }
 
   if (warp == 4 && lane == 0 && p.w_resident && (int)blockIdx.x < total_tiles)
@@ -565,10 +724,28 @@ static int plan_max_rows(const KtConv1dDesc* d, int dir);
 
 // shared memory outside the activation / weight stages: barriers, TMEM slot, tap-shift table, epilogue transposition
 // + bias tiles (see the carve-up in conv_tc_kernel)
-static int tc_fixed_smem(int slots) { return (2 * 3 + 2 * std::max(6, slots) + 4) * 8 + 16 + kMaxTaps * 4 + 8 * 2048 + 8 * 1024; }
+static int tc_fixed_smem(int slots, bool epi_tma = false, bool epi_alias = false) {
+  return (2 * 3 + 2 * std::max(6, slots) + 4) * 8 + 16 + kMaxTaps * 4 + (epi_alias ? 0 : (epi_tma ? 8 * kEpiBufs * kEpiBufBytes : 8 * 2048)) +
+         8 * 1024 + 8 * kEpiBufs * 8;
+}
+static bool epi_tma_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("KANTTS_B200_EPI_TMA");
+    return !(e && e[0] == '0') && encode_tiled_fn() != nullptr;
+  }();
+  return on;
+}
 // can a (rows, NT) tiling run with at least two activation and two weight stages?
 static bool tc_ring_fits(int rows, int NT) {
   return 2 * (2 * rows * 128) + 2 * (2 * NT * 128) <= kMaxDynSmem - 1024 - tc_fixed_smem(0);
+}
+
+static int sm_count();
+
+// one phase writing consecutive output rows from row 0 (every forward of a plain conv, the data gradient of a stride-1 conv)
+static bool plain_single_phase(const KtConv1dDesc* d, int dir) {
+  const std::vector<Phase> ph = conv_phases(d, dir);
+  return ph.size() == 1 && ph[0].o_step == 1 && ph[0].o_off == 0 && !ph[0].accumulate;
 }
 
 static TcLayerPlan layer_plan(const KtConv1dDesc* d, int dir) {
@@ -602,6 +779,9 @@ static TcLayerPlan layer_plan(const KtConv1dDesc* d, int dir) {
     const long long mtiles = (long long)ceil_div((dir == 0 ? d->t_out : d->t_in) * d->nsub, kTcM) * d->batch;
     if (L.NT == 256 && mtiles * (pout / 256) < 120) L.NT = 128;
     if (L.NT == 256 && !tc_ring_fits(plan_max_rows(d, dir), 256)) L.NT = 128;   // long-halo (strided) layers: 64 KB weight stages do not fit
+    // TMA epilogue: its boxes take the room of one 64 KB stage -- unless every CTA gets at most one tile (the boxes then
+    // reuse the idle operand stages, epi_alias)
+    if (L.NT == 256 && epi_tma_enabled() && plain_single_phase(d, dir) && mtiles * (pout / 256) > sm_count()) L.NT = 128;
     L.n_stride = L.NT; L.ntiles = pout / L.NT;
   }
   L.ok = true;
@@ -744,8 +924,38 @@ static int run_tc(TcParams p, cudaStream_t st) {   // p: phases already planned 
   const int a_stage = 2 * p.rows * 128;
   const int b_stage = 2 * p.NT * 128;
   const int slots = p.ntaps * p.kchunks;                                      // weight tiles of the whole layer
-  const int bar_bytes = tc_fixed_smem(slots);
+  // TMA epilogue: one phase of consecutive output rows, whole 16-column boxes inside this tile's channel range (or past the
+  // tensor's last channel, where the TMA unit clips), at most one side operand, room for two image + two weight stages
+  const float* side_ptr = p.resid ? p.resid : p.mask.p;
+  const long long tiles = (long long)p.ph_mt0[p.nphases] * p.ntiles * p.batch;
+  const bool one_tile = tiles <= sm_count();
+  p.epi_tma = (epi_tma_enabled() && p.nphases == 1 && p.o_step == 1 && p.ph_ooff[0] == 0 && !p.accumulate && p.ph_M[0] == p.t_out &&
+               (p.c_out & 3) == 0 && (p.ntiles == 1 || p.n_stride == p.NT) && !(p.resid && p.mask.p) &&
+               (!p.mask.p || p.mask.mode == SIDE_DLRELU) && (p.NT & 15) == 0 &&
+               2 * a_stage + 2 * b_stage <= kMaxDynSmem - 1024 - tc_fixed_smem(slots, true, one_tile) &&
+               (!one_tile || 2 * a_stage + 2 * b_stage >= 8 * kEpiBufs * kEpiBufBytes)) ? 1 : 0;
+  p.epi_split = (p.epi_tma && (p.NT & 31) == 0) ? 1 : 0;
+  p.epi_alias = (p.epi_tma && one_tile) ? 1 : 0;
+  const int bar_bytes = tc_fixed_smem(slots, p.epi_tma != 0, p.epi_alias != 0);
   const int budget = kMaxDynSmem - 1024 /*align slack*/ - bar_bytes;
+  if (p.epi_tma) {
+    // (cuTensorMapEncodeTiled is a driver call: it needs the primary context bound to THIS thread -- backward launches come from
+    //  autograd engine threads that may not have made a runtime call yet; any runtime call binds it, this one is capture-safe)
+    cudaStreamCaptureStatus cap;
+    KT_CHECK_CUDA(cudaStreamIsCapturing(st, &cap));
+    const cuuint64_t rows_item = (cuuint64_t)p.t_out * p.nsub;
+    const cuuint64_t gdim[3] = {(cuuint64_t)p.c_out, rows_item, (cuuint64_t)p.batch};
+    const cuuint64_t gstr[2] = {(cuuint64_t)p.c_out * 4, rows_item * p.c_out * 4};
+    const cuuint32_t box[3] = {16, 32, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode_tiled_fn()(&p.map_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p.out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_SUCCESS && side_ptr)
+      r = encode_tiled_fn()(&p.map_side, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(side_ptr), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    KT_REQUIRE(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled (epilogue) failed (%d)", (int)r);
+  }
   p.w_resident = 0;
   if (p.ntiles == 1 && slots <= 160 && 2 * a_stage + slots * b_stage <= budget) {
     p.w_resident = 1;
@@ -770,7 +980,6 @@ static int run_tc(TcParams p, cudaStream_t st) {   // p: phases already planned 
     KT_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
     cfg.store(true, std::memory_order_release);
   }
-  const long long tiles = (long long)p.ph_mt0[p.nphases] * p.ntiles * p.batch;
   const int grid = (int)std::min<long long>(tiles, sm_count());
   const bool simple = p.nsub == 1 && p.up == 1 && (p.kg & 7) == 0 && (p.c_in & 3) == 0 && (p.c_out & 3) == 0 &&
                       (p.n_stride & 3) == 0 && p.out_act != KT_ACT_TANH && !p.accumulate &&

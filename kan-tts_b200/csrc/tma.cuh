@@ -32,5 +32,23 @@ __device__ __forceinline__ void tma_load_5d(void* dst_smem, const CUtensorMap* m
       : "memory");
 }
 
+// one 3-D box global -> shared
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(dst_smem)),
+               "l"(map), "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// one 3-D box shared -> global (SASS UTMASTG), bulk async-group completion; elements outside the tensor are not written
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the N most recent bulk groups of this thread have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
 }  // namespace tc
 }  // namespace kt

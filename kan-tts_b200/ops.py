@@ -219,7 +219,10 @@ def prepare_weight(cache, spec, v, g):
     # call runs under no_grad, so `is_leaf` must not decide this: such a weight is never cached and always gets fresh
     # buffers (a pending backward of the other half of a (generated, real) pair still holds the previous ones).
     cacheable = isinstance(v, torch.nn.Parameter) and (g is None or isinstance(g, torch.nn.Parameter))
-    key = (v.data_ptr(), v._version, None if g is None else (g.data_ptr(), g._version)) if cacheable else None
+    # (_version alone is not enough: torch's fused Adam -- and any optimizer that updates through its own kernels -- leaves it
+    #  untouched, so every optimizer step also bumps a per-parameter epoch, see _bump_param_epochs)
+    key = (v.data_ptr(), v._version, getattr(v, "_kt_epoch", 0),
+           None if g is None else (g.data_ptr(), g._version, getattr(g, "_kt_epoch", 0))) if cacheable else None
     if key is not None and cache.key == key and cache.w_fwd is not None and cache.w_fwd.device == v.device:
         return cache
     lib = _lib.load()
@@ -249,6 +252,20 @@ def prepare_weight(cache, spec, v, g):
     cache.img_stale = set(cache.img)      # packed tcgen05 tiles are re-packed (in place) on next use
     return cache
 
+
+def _bump_param_epochs(optimizer, args, kwargs):
+    """Global optimizer-step post hook: every parameter the optimizer owns gets a new epoch, which invalidates the prepared
+    (kernel-layout) copies of its layer.  Found by tests/test_gpu_graph.py: with ``torch.optim.Adam(fused=True)`` the eager
+    step kept running on the weights of step 0 (``Tensor._version`` does not move) while the CUDA-graph step, which
+    re-prepares unconditionally, was right."""
+    for group in optimizer.param_groups:
+        for p in group["params"]:
+            p._kt_epoch = getattr(p, "_kt_epoch", 0) + 1
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _register_post_hook  # noqa: E402
+
+_register_post_hook(_bump_param_epochs)
 
 _grad_items = None
 

@@ -9,7 +9,7 @@ for leg in "$@"; do
     unverified) KANTTS_B200_TEST_UNVERIFIED=1 timeout 600 python -m pytest tests/test_gpu_pipeline.py -m gpu -q --tb=short > gpurun_out/unverified_$TAG.log 2>&1; echo "unverified rc=$?" >> $S
            grep -E "passed|failed|^FAILED|^ERROR" gpurun_out/unverified_$TAG.log | cut -c1-300 | head -30 >> $S ;;
     trace) timeout 300 python scripts/tc_trace.py > gpurun_out/tc_trace_$TAG.log 2>&1; echo "trace rc=$?" >> $S ;;
-    layers) timeout 300 python scripts/layer_bench.py > gpurun_out/layers_$TAG.log 2>&1; echo "layers rc=$?" >> $S ;;
+    layers) KANTTS_B200_WGRAD_STREAMS=0 timeout 300 python scripts/layer_bench.py > gpurun_out/layers_$TAG.log 2>&1; echo "layers rc=$?" >> $S ;;
     smoke) timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?" >> $S ;;
     bench) timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.log 2>&1; echo "bench rc=$?" >> $S ;;
     breakdown) timeout 600 python scripts/breakdown.py > gpurun_out/breakdown_$TAG.log 2>&1; echo "breakdown rc=$?" >> $S ;;
