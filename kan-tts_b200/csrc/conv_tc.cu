@@ -178,15 +178,18 @@ __device__ __forceinline__ void epilogue_tma(const TcParams& p, uint32_t tmem_ac
     const int c_tile = nt * p.n_stride;
     const int n_valid = min(p.n_stride, p.c_out - c_tile);
     if (tracer) trace_ev(p, 3, ti, 0);
-    if (side_kind && lane == 0) {   // side boxes of the first two column blocks (their buffers: last read by stores k-3 and k-2)
-      bulk_wait_group_read<1>();
-      for (int j = 0; j < 2; ++j)
-        if (h_begin + j < h_end) {
-          const uint32_t b = (k + j) % kEpiBufs;
-          mbar_arrive_expect_tx(&ebar[b], (uint32_t)kEpiBufBytes);
-          tma_load_3d(ebuf + b * kEpiBufBytes, &p.map_side, c_tile + (h_begin + j) * 16, r0, bb, &ebar[b]);
-        }
-    }
+    auto side_prefetch = [&]() {    // side boxes of the first two column blocks (their buffers: last read by stores k-3 and k-2)
+      if (side_kind && lane == 0) {
+        bulk_wait_group_read<1>();
+        for (int j = 0; j < 2; ++j)
+          if (h_begin + j < h_end) {
+            const uint32_t b = (k + j) % kEpiBufs;
+            mbar_arrive_expect_tx(&ebar[b], (uint32_t)kEpiBufBytes);
+            tma_load_3d(ebuf + b * kEpiBufBytes, &p.map_side, c_tile + (h_begin + j) * 16, r0, bb, &ebar[b]);
+          }
+      }
+    };
+    if (!p.epi_alias) side_prefetch();   // (aliased boxes ARE operand stages: nothing may land there before the tile's MMAs are done)
     if (p.bias) {
       __syncwarp();
       for (int e = lane; e < p.NT; e += 32) sbias[e] = e < n_valid ? __ldg(p.bias + c_tile + e) : 0.f;
@@ -194,6 +197,7 @@ __device__ __forceinline__ void epilogue_tma(const TcParams& p, uint32_t tmem_ac
     }
     mbar_wait(&tmem_full[buf], (ti >> 1) & 1);
     tc_fence_after();
+    if (p.epi_alias) side_prefetch();
     if (tracer) trace_ev(p, 3, ti, 1);
     const uint32_t t_lane = tmem_acc + (uint32_t)buf * buf_cols + ((uint32_t)(quarter * 32) << 16);
     for (int hh = h_begin; hh < h_end; hh += 2) {
@@ -968,8 +972,9 @@ static int run_tc(TcParams p, cudaStream_t st) {   // p: phases already planned 
     // on one image for its successor to be staged meanwhile: they give the third image stage to the weight ring.
     int min_taps = kMaxTaps;
     for (int g = 0; g < p.ngroups; ++g) min_taps = std::min(min_taps, p.grp_first[g + 1] - p.grp_first[g]);
-    p.na_stages = (min_taps >= 4 && !tc_env_flag("KANTTS_B200_TC_NA3")) ? 2 : 3;
-    if (3 * a_stage + 3 * b_stage > budget) p.na_stages = 2;
+    // (three of each when they fit -- single-tile launches, whose epilogue boxes reuse the stages)
+    p.na_stages = (3 * a_stage + 3 * b_stage <= budget) ? 3 : ((min_taps >= 4 && !tc_env_flag("KANTTS_B200_TC_NA3")) ? 2 : 3);
+    if (3 * a_stage + 2 * b_stage > budget) p.na_stages = 2;
     p.nb_stages = std::min(6, (budget - p.na_stages * a_stage) / b_stage);
   }
   KT_REQUIRE(p.nb_stages >= 2 || p.w_resident, "conv_tc: shared memory budget exceeded (rows=%d NT=%d)", p.rows, p.NT);
