@@ -130,6 +130,131 @@ __global__ void __launch_bounds__(256) thin_cin1_wgrad_kernel(const ThinParams p
   }
 }
 
+// ---- the scale discriminator's first layer (Conv1d(1, 128, 15), stride 1, one sub-sequence) ---------------------------------
+// The generic kernels above re-read the k taps' weights from shared memory (forward: 15 LDS.128 per output quad, ~1 GB of
+// shared-memory traffic per launch) or the k input samples (weight gradient: 15 loads per element) for every output row:
+// 91 us / 292 us per B = 16 launch against 11 us / 22 us of HBM time (call r2ak).  Here a WARP owns a run of consecutive
+// rows of one item and a lane owns one channel quad for the whole kernel: weights (forward) / gradient accumulators
+// (weight gradient) live in registers, the input window of a block of 8 rows is 8 + k - 1 warp-uniform loads.
+constexpr int kThinRW = 64;   // rows per warp task
+constexpr int kThinUR = 8;    // rows per register block
+
+template <int K>
+__global__ void __launch_bounds__(256) thin_c128_fwd_kernel(const ThinParams p) {
+  const int lane = threadIdx.x & 31, c = lane * 4;
+  const int gwarp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+  float4 w[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) w[j] = __ldg(reinterpret_cast<const float4*>(p.w + j * 128 + c));
+  const float4 bv = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int tasks_item = (p.t_out + kThinRW - 1) / kThinRW;
+  for (int task = gwarp; task < p.batch * tasks_item; task += nwarps) {
+    const int b = task / tasks_item, t0 = (task - b * tasks_item) * kThinRW;
+    const float* xb = p.x + (long long)b * p.t_in;
+    float* ob = p.out + ((long long)b * p.t_out) * 128 + c;
+    const int t1 = min(p.t_out, t0 + kThinRW);
+    for (int tb = t0; tb < t1; tb += kThinUR) {
+      float xw[kThinUR + K - 1];
+#pragma unroll
+      for (int i = 0; i < kThinUR + K - 1; ++i) {
+        const int ti = tb - p.pad + i;
+        xw[i] = (ti >= 0 && ti < p.t_in) ? __ldg(xb + ti) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kThinUR; ++u) {
+        if (tb + u < t1) {
+          float4 acc = bv;
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            acc.x = fmaf(xw[u + j], w[j].x, acc.x); acc.y = fmaf(xw[u + j], w[j].y, acc.y);
+            acc.z = fmaf(xw[u + j], w[j].z, acc.z); acc.w = fmaf(xw[u + j], w[j].w, acc.w);
+          }
+          if (p.act == KT_ACT_LRELU) {
+            acc.x = acc.x > 0.f ? acc.x : acc.x * p.slope; acc.y = acc.y > 0.f ? acc.y : acc.y * p.slope;
+            acc.z = acc.z > 0.f ? acc.z : acc.z * p.slope; acc.w = acc.w > 0.f ? acc.w : acc.w * p.slope;
+          }
+          *reinterpret_cast<float4*>(ob + (long long)(tb + u) * 128) = acc;
+        }
+      }
+    }
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(256) thin_c128_wgrad_kernel(const ThinParams p) {
+  __shared__ float4 red[4][K + 1][32];   // two rounds: warps 4-7 -> 0-3, then 0-3 -> the atomics
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, c = lane * 4;
+  const int gwarp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nwarps = (int)((gridDim.x * blockDim.x) >> 5);
+  float4 acc[K + 1];
+#pragma unroll
+  for (int j = 0; j <= K; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int tasks_item = (p.t_out + kThinRW - 1) / kThinRW;
+  for (int task = gwarp; task < p.batch * tasks_item; task += nwarps) {
+    const int b = task / tasks_item, t0 = (task - b * tasks_item) * kThinRW;
+    const float* xb = p.x + (long long)b * p.t_in;
+    const long long rb = ((long long)b * p.t_out) * 128 + c;
+    const int t1 = min(p.t_out, t0 + kThinRW);
+    for (int tb = t0; tb < t1; tb += kThinUR) {
+      float4 g[kThinUR];
+#pragma unroll
+      for (int u = 0; u < kThinUR; ++u) {
+        const bool ok = tb + u < t1;
+        g[u] = ok ? __ldg(reinterpret_cast<const float4*>(p.dy + rb + (long long)(tb + u) * 128)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && p.act == KT_ACT_LRELU) {
+          const float4 yv = __ldg(reinterpret_cast<const float4*>(p.y + rb + (long long)(tb + u) * 128));
+          g[u].x = yv.x > 0.f ? g[u].x : g[u].x * p.slope; g[u].y = yv.y > 0.f ? g[u].y : g[u].y * p.slope;
+          g[u].z = yv.z > 0.f ? g[u].z : g[u].z * p.slope; g[u].w = yv.w > 0.f ? g[u].w : g[u].w * p.slope;
+        }
+      }
+      float xw[kThinUR + K - 1];
+#pragma unroll
+      for (int i = 0; i < kThinUR + K - 1; ++i) {
+        const int ti = tb - p.pad + i;
+        xw[i] = (ti >= 0 && ti < p.t_in) ? __ldg(xb + ti) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kThinUR; ++u) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          acc[j].x = fmaf(xw[u + j], g[u].x, acc[j].x); acc[j].y = fmaf(xw[u + j], g[u].y, acc[j].y);
+          acc[j].z = fmaf(xw[u + j], g[u].z, acc[j].z); acc[j].w = fmaf(xw[u + j], g[u].w, acc[j].w);
+        }
+        acc[K].x += g[u].x; acc[K].y += g[u].y; acc[K].z += g[u].z; acc[K].w += g[u].w;
+      }
+    }
+  }
+  if (warp >= 4) {
+#pragma unroll
+    for (int j = 0; j <= K; ++j) red[warp - 4][j][lane] = acc[j];
+  }
+  __syncthreads();
+  if (warp < 4) {
+#pragma unroll
+    for (int j = 0; j <= K; ++j) {
+      const float4 o = red[warp][j][lane];
+      acc[j].x += o.x; acc[j].y += o.y; acc[j].z += o.z; acc[j].w += o.w;
+    }
+  }
+  __syncthreads();
+  if (warp < 4) {
+#pragma unroll
+    for (int j = 0; j <= K; ++j) red[warp][j][lane] = acc[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (K + 1) * 128; i += blockDim.x) {
+    const int j = i >> 7, cc = i & 127;
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s += reinterpret_cast<const float*>(&red[q][j][0])[cc];
+    if (j < K) atomicAdd(p.out + j * 128 + cc, s);
+    else if (p.dbias) atomicAdd(p.dbias + cc, s);
+  }
+}
+
+static bool thin_c128_ok(const KtConv1dDesc* d) {
+  return d->nsub == 1 && d->stride == 1 && d->dilation == 1 && d->c_out == 128 && (d->kernel == 15 || d->kernel == 5 || d->kernel == 3);
+}
+
 int thin_cin1_fwd(const KtConv1dDesc* d, const float* x, const float* w_fwd, const float* bias, float* y, cudaStream_t st) {
   ThinParams p{};
   p.x = x; p.w = w_fwd; p.bias = bias; p.out = y;
@@ -137,6 +262,15 @@ int thin_cin1_fwd(const KtConv1dDesc* d, const float* x, const float* w_fwd, con
   p.stride = d->stride; p.dil = d->dilation; p.pad = d->pad_left; p.act = d->act_out; p.slope = d->act_out_slope;
   const long long total = (long long)d->batch * d->t_out * d->nsub * (d->c_out / 4);
   KT_REQUIRE(total < (1LL << 31), "thin_cin1_fwd: tensor too large for 32-bit row indexing");
+  if (thin_c128_ok(d)) {
+    const long long tasks = (long long)d->batch * ((d->t_out + kThinRW - 1) / kThinRW);
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((tasks + 7) / 8, 148LL * 4));
+    if (d->kernel == 15) thin_c128_fwd_kernel<15><<<blocks, 256, 0, st>>>(p);
+    else if (d->kernel == 5) thin_c128_fwd_kernel<5><<<blocks, 256, 0, st>>>(p);
+    else thin_c128_fwd_kernel<3><<<blocks, 256, 0, st>>>(p);
+    KT_CHECK_CUDA(cudaGetLastError());
+    return KT_OK;
+  }
   const int blocks = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, 148LL * 16));   // 256 % (c_out/4) == 0
   const size_t smem = (size_t)(d->kernel + 1) * d->c_out * sizeof(float);
   thin_cin1_fwd_kernel<<<blocks, 256, smem, st>>>(p);
@@ -153,6 +287,15 @@ int thin_cin1_wgrad(const KtConv1dDesc* d, const float* x, const float* dy, cons
   KT_REQUIRE((long long)d->batch * d->t_out * d->nsub < (1LL << 31), "thin_cin1_wgrad: tensor too large for 32-bit row indexing");
   KT_CHECK_CUDA(cudaMemsetAsync(dw, 0, (size_t)d->kernel * d->c_out * sizeof(float), st));
   if (dbias) KT_CHECK_CUDA(cudaMemsetAsync(dbias, 0, (size_t)d->c_out * sizeof(float), st));
+  if (thin_c128_ok(d)) {
+    const long long tasks = (long long)d->batch * ((d->t_out + kThinRW - 1) / kThinRW);
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((tasks + 7) / 8, 148LL));
+    if (d->kernel == 15) thin_c128_wgrad_kernel<15><<<blocks, 256, 0, st>>>(p);
+    else if (d->kernel == 5) thin_c128_wgrad_kernel<5><<<blocks, 256, 0, st>>>(p);
+    else thin_c128_wgrad_kernel<3><<<blocks, 256, 0, st>>>(p);
+    KT_CHECK_CUDA(cudaGetLastError());
+    return KT_OK;
+  }
   const long long rows = (long long)d->batch * d->t_out * d->nsub;
   const int nslots = 256 / d->c_out;
   long long ctas = std::min<long long>(148LL * 4, std::max<long long>(1, rows / (nslots * 32LL)));
