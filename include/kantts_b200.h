@@ -193,6 +193,9 @@ int kt_stft_mel_bwd(const KtMelDesc* d, const float* dmel, const float* damp, co
 
 /* out[0] = scale * sum |a - b|  (F.l1_loss numerator; loss.py:249,309); out[0] is overwritten. */
 int kt_l1_sum(const float* a, const float* b, int64_t n, float scale, float* out, void* stream);
+/* out[0] += scale * sum |a - b|: one accumulator for a whole feature pyramid (FeatureMatchLoss, loss.py:217-256); the caller
+ * zeroes out[0] once. */
+int kt_l1_sum_acc(const float* a, const float* b, int64_t n, float scale, float* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SAM-BERT acoustic model (kantts/models/sambert).  Activations are (B, L, C) rows -- the

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "kt_stft_mel_fwd": [ctypes.POINTER(KtMelDesc), _P, _P, _P, _P, _P, _P, _P],
     "kt_stft_mel_bwd": [ctypes.POINTER(KtMelDesc), _P, _P, _P, _P, _P, _P, _P],
     "kt_l1_sum": [_P, _P, _L, _F, _P, _P],
+    "kt_l1_sum_acc": [_P, _P, _L, _F, _P, _P],
     "kt_conv1d_tc_plan": [ctypes.POINTER(KtConv1dDesc), _I],
     "kt_conv1d_tc_image_bytes": [ctypes.POINTER(KtConv1dDesc), _I],
     "kt_weight_pack_tc": [ctypes.POINTER(KtConv1dDesc), _I, _P, _P, _P],

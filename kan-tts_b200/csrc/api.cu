@@ -16,7 +16,7 @@ int add3_scale(const float*, const float*, const float*, float, float*, long lon
 int upsample_grad_reduce(const float*, const float*, int, float, float*, long long, int, int, cudaStream_t);
 int dwt_fwd(const float*, float*, int, int, cudaStream_t);
 int dwt_bwd(const float*, float*, int, int, cudaStream_t);
-int l1_sum(const float*, const float*, long long, float, float*, cudaStream_t);
+int l1_sum(const float*, const float*, long long, float, float*, cudaStream_t, bool accumulate = false);
 int stft_mel_fwd(const KtMelDesc*, const float*, const float*, const float*, float*, float*, float*, cudaStream_t);
 int stft_mel_bwd(const KtMelDesc*, const float*, const float*, const float*, const float*, const float*, float*, cudaStream_t);
 long long wgrad_tc_workspace(const KtConv1dDesc*);
@@ -129,6 +129,9 @@ int kt_stft_mel_bwd(const KtMelDesc* d, const float* dmel, const float* damp, co
 }
 int kt_l1_sum(const float* a, const float* b, int64_t n, float scale, float* out, void* stream) {
   return kt::l1_sum(a, b, n, scale, out, ST(stream));
+}
+int kt_l1_sum_acc(const float* a, const float* b, int64_t n, float scale, float* out, void* stream) {
+  return kt::l1_sum(a, b, n, scale, out, ST(stream), true);
 }
 
 const char* kt_last_error(void) { return kt::last_error(); }

@@ -130,7 +130,14 @@ __global__ void dwt_bwd_kernel(const float* __restrict__ dy, float* __restrict__
 
 __global__ void l1_sum_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float scale, float* out) {
   float acc = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+  const long long gtid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
+  const bool vec = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+  const long long n4 = vec ? n / 4 : 0;
+  for (long long i = gtid; i < n4; i += gsz) {
+    const float4 u = __ldg(reinterpret_cast<const float4*>(a) + i), v = __ldg(reinterpret_cast<const float4*>(b) + i);
+    acc += fabsf(u.x - v.x) + fabsf(u.y - v.y) + fabsf(u.z - v.z) + fabsf(u.w - v.w);
+  }
+  for (long long i = n4 * 4 + gtid; i < n; i += gsz)
     acc += fabsf(__ldg(a + i) - __ldg(b + i));
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   __shared__ float red[8];
@@ -178,11 +185,11 @@ int dwt_bwd(const float* dy, float* dx, int batch, int t, cudaStream_t st) {
   KT_CHECK_CUDA(cudaGetLastError());
   return KT_OK;
 }
-int l1_sum(const float* a, const float* b, long long n, float scale, float* out, cudaStream_t st) {
+int l1_sum(const float* a, const float* b, long long n, float scale, float* out, cudaStream_t st, bool accumulate) {
   KT_REQUIRE(a && b && out && n >= 0, "l1_sum: bad arguments");
-  KT_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+  if (!accumulate) KT_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
   if (n == 0) return KT_OK;
-  l1_sum_kernel<<<stream_grid(n, 256), 256, 0, st>>>(a, b, n, scale, out);
+  l1_sum_kernel<<<stream_grid(n / 4 + 1, 256), 256, 0, st>>>(a, b, n, scale, out);
   KT_CHECK_CUDA(cudaGetLastError());
   return KT_OK;
 }

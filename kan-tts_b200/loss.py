@@ -43,6 +43,24 @@ class _AdversarialBase(torch.nn.Module):
         total = sum(terms[1:], terms[0])
         return total / len(terms) if self.average_by_discriminators and len(terms) > 1 else total
 
+    _weights = {}
+
+    def _mse_total(self, outs, target):
+        """sum_i mean((o_i - target)^2) [/ n] as ONE chain over the concatenated logits: cat, sub, mul, dot (and their four
+        backward kernels) instead of ~10 tiny launches per sub-discriminator -- the loss sits on the critical path between
+        the discriminators' forward and backward passes.  Per-element weights 1 / numel_i are cached per shape set."""
+        outs = [o.reshape(-1) for o in outs]
+        if len(outs) == 1 or not outs[0].is_cuda:
+            return self._reduce([torch.mean((o - target) ** 2) for o in outs])
+        key = (tuple(o.numel() for o in outs), outs[0].device, bool(self.average_by_discriminators))
+        w = self._weights.get(key)
+        if w is None:
+            scale = 1.0 / len(outs) if self.average_by_discriminators else 1.0
+            w = torch.cat([torch.full((o.numel(),), scale / o.numel(), dtype=torch.float32) for o in outs]).to(outs[0].device)
+            self._weights[key] = w
+        d = torch.cat(outs) - target
+        return torch.dot(d * w, d)
+
 
 class GeneratorAdversarialLoss(_AdversarialBase):
     """kantts/train/loss.py:108-145: the generator wants every sub-discriminator to call its output real
@@ -50,9 +68,8 @@ class GeneratorAdversarialLoss(_AdversarialBase):
 
     def forward(self, outputs):
         if self.loss_type == "mse":
-            terms = [_gan_term(o, 1.0, "mse") for o in _as_list(outputs)]
-        else:
-            terms = [-torch.mean(o) for o in _as_list(outputs)]
+            return self._mse_total(_as_list(outputs), 1.0)
+        terms = [-torch.mean(o) for o in _as_list(outputs)]
         return self._reduce(terms)
 
 
@@ -61,6 +78,9 @@ class DiscriminatorAdversarialLoss(_AdversarialBase):
     (mse) or past the +-1 margins (hinge)."""
 
     def forward(self, outputs_hat, outputs):
+        if self.loss_type == "mse":
+            return (self._mse_total([_last(o) for o in _as_list(outputs)], 1.0),
+                    self._mse_total([_last(o) for o in _as_list(outputs_hat)], 0.0))
         fake = [_gan_term(_last(o), 0.0, self.loss_type) for o in _as_list(outputs_hat)]
         real = [_gan_term(_last(o), 1.0, self.loss_type) for o in _as_list(outputs)]
         return self._reduce(real), self._reduce(fake)
@@ -80,6 +100,17 @@ def _l1_mean(a, b):
     return ops.l1_sum(a.detach(), b.detach(), 1.0 / a.numel())
 
 
+def _rows_pair(a, b):
+    """-> the contiguous channels-last buffers behind two feature-map views of this package, or None."""
+    if a.requires_grad or not a.is_cuda or a.shape != b.shape:
+        return None
+    if a.dim() == 3 and not a.is_contiguous():
+        a, b = a.transpose(1, 2), b.transpose(1, 2)
+    elif a.dim() == 4 and not a.is_contiguous():
+        a, b = a.permute(0, 2, 3, 1), b.permute(0, 2, 3, 1)
+    return (a.detach(), b.detach()) if a.is_contiguous() and b.is_contiguous() else None
+
+
 class FeatureMatchLoss(torch.nn.Module):
     """kantts/train/loss.py:217-256: sum over sub-discriminators of the (summed or averaged) per-layer L1 distance
     between two feature-map pyramids; the second argument is treated as a constant."""
@@ -90,6 +121,9 @@ class FeatureMatchLoss(torch.nn.Module):
         self.average_by_discriminators = average_by_discriminators
 
     def forward(self, feats_hat, feats):
+        fast = self._forward_accumulated(feats_hat, feats)
+        if fast is not None:
+            return fast
         per_disc = []
         for maps_hat, maps in zip(feats_hat, feats):
             layer_terms = [_l1_mean(a, b) for a, b in zip(maps_hat, maps)]
@@ -161,6 +195,33 @@ class MultiResolutionSTFTLoss(torch.nn.Module):
         n = len(terms)
         return sum(t[0] for t in terms) / n, sum(t[1] for t in terms) / n
 
+
+def _fm_forward_accumulated(self, feats_hat, feats):
+    """Value-only pyramids (the trainer's use, see the module docstring): every layer's weighted L1 sum goes into ONE device
+    accumulator -- one launch per feature map instead of memset + kernel + the add / divide chain of the generic path."""
+    pairs, scales = [], []
+    n_disc = len(feats_hat)
+    for maps_hat, maps in zip(feats_hat, feats):
+        for a, b in zip(maps_hat, maps):
+            rp = _rows_pair(a, b)
+            if rp is None:
+                return None
+            pairs.append(rp)
+            s = 1.0 / rp[0].numel()
+            if self.average_by_layers:
+                s /= len(maps_hat)
+            if self.average_by_discriminators:
+                s /= n_disc
+            scales.append(s)
+    if not pairs:
+        return None
+    out = torch.zeros((), device=pairs[0][0].device, dtype=torch.float32)
+    for (a, b), s in zip(pairs, scales):
+        ops.l1_sum_acc(out, a, b, s)
+    return out
+
+
+FeatureMatchLoss._forward_accumulated = _fm_forward_accumulated
 
 loss_dict = {
     "generator_adv_loss": GeneratorAdversarialLoss,

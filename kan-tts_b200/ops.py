@@ -792,6 +792,13 @@ class StftMelFn(torch.autograd.Function):
         return dwav, None, None, None, None, None, None, None
 
 
+def l1_sum_acc(out, a, b, scale):
+    """out += scale * sum|a - b| (0-dim device accumulator zeroed by the caller; one launch)."""
+    a, b = a.contiguous(), b.contiguous()
+    check(_lib.load().kt_l1_sum_acc(ptr(a), ptr(b), a.numel(), float(scale), ptr(out), stream_ptr()), "kt_l1_sum_acc")
+    _count()
+
+
 def l1_sum(a, b, scale=1.0):
     """scale * sum|a - b| -> 0-dim tensor (no autograd; feature-matching value, loss.py:249)."""
     a, b = a.contiguous(), b.contiguous()

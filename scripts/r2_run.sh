@@ -30,6 +30,7 @@ for leg in "$@"; do
     ncu_rb) timeout 600 ncu --set full --clock-control none --import-source on -k regex:resblock_tc_kernel -s 2 -c 1 -f -o gpurun_out/ncu_resblock_$TAG env RB_ONLY_BIG=1 python scripts/rb_test.py > gpurun_out/ncu_rb_$TAG.log 2>&1; echo "ncu_rb rc=$?" >> $S ;;
     ablayers) for F in 0 16 32 48 64 80 96 112; do timeout 200 python scripts/layer_bench.py --flags $F --only ${AB_LAYERS:-gen_128_128_k11,mpd_1024_1024_k5_p3,msd_1024_1024_k5,gen_32_32_k7,mpd_128_512_k5s3_p5} >> gpurun_out/ablayers_$TAG.log 2>&1; done; echo "ablayers rc=$?" >> $S ;;
     ncu_layers) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/ncu_layers_$TAG.csv python scripts/layer_bench.py --iters 1 ${NCU_LAYERS:+--only $NCU_LAYERS} > gpurun_out/ncu_layers_$TAG.log 2>&1; echo "ncu_layers rc=$?" >> $S ;;
+    torchops) timeout 600 python scripts/torch_ops_profile.py > gpurun_out/torchops_$TAG.log 2>&1; echo "torchops rc=$?" >> $S ;;
     ablate) timeout 900 python scripts/ablate_step.py > gpurun_out/ablate_$TAG.log 2>&1; echo "ablate rc=$?" >> $S; grep -E "ms" gpurun_out/ablate_$TAG.log >> $S ;;
     *) echo "unknown leg $leg" >> $S ;;
   esac
