@@ -477,24 +477,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
               if (p.dbg & 64) {
                 // ablation: no MMAs (pipelines and commits only)
               } else if (fuse2) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  if (kk < kslices) {
-                    umma_bf16_lo(d_tmem, a_hi + 2u * kk, b_hi + 2u * kk, idesc2, acc);       // [a_hi*b_hi | a_hi*b_lo] -> columns [0, 2*NT)
-                    umma_bf16_lo(d_tmem, a_hi + img16 + 2u * kk, b_hi + 2u * kk, idesc, 1u);  //  a_lo*b_hi             -> columns [0, NT)
-                    acc = 1;
-                  }
-                }
+                umma_step_fuse2(d_tmem, a_hi, img16, b_hi, idesc2, idesc, acc, (uint32_t)kslices);
+                acc = 1;
               } else {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  if (kk < kslices) {
-                    umma_bf16_lo(d_tmem, a_hi + img16 + 2u * kk, b_hi + 2u * kk, idesc, acc);
-                    umma_bf16_lo(d_tmem, a_hi + 2u * kk, b_hi + bplane16 + 2u * kk, idesc, 1u);
-                    umma_bf16_lo(d_tmem, a_hi + 2u * kk, b_hi + 2u * kk, idesc, 1u);
-                    acc = 1;
-                  }
-                }
+                umma_step_x3(d_tmem, a_hi, img16, b_hi, bplane16, idesc, acc, (uint32_t)kslices);
+                acc = 1;
               }
               if (!resident) umma_commit(&empty_b[sb]);
             }

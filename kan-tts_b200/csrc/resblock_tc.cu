@@ -356,14 +356,8 @@ __global__ void __launch_bounds__(kRbThreads, 1) resblock_tc_kernel(const __grid
           const uint32_t a_hi = a16 + (uint32_t)s * astep;
           const uint32_t b_hi = w16 + (uint32_t)slot * tile16;
           const int ks = (s == p.nsteps - 1) ? p.last_kslices : 4;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            if (kk < ks) {
-              umma_bf16_lo(d_tmem, a_hi + 2u * kk, b_hi + 2u * kk, idesc2, acc);               // [a_hi*b_hi | a_hi*b_lo]
-              umma_bf16_lo(d_tmem, a_hi + plane16 + 2u * kk, b_hi + 2u * kk, idesc, 1u);       //  a_lo*b_hi
-              acc = 1;
-            }
-          }
+          umma_step_fuse2(d_tmem, a_hi, plane16, b_hi, idesc2, idesc, acc, (uint32_t)ks);   // per slice: [a_hi*b_hi | a_hi*b_lo], a_lo*b_hi
+          acc = 1;
           if (!p.resident) umma_commit(&w_empty[slot]);
         }
       };

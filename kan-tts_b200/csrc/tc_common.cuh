@@ -116,6 +116,66 @@ __device__ __forceinline__ void umma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uin
       "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHiSw128)
       : "memory");
 }
+// All MMAs of one (tap, K chunk) step in ONE asm block: `ks` (1..4) K = 16 slices, the descriptor low words advance by 2 (32 bytes)
+// per slice.  Issued one by one through umma_bf16_lo the compiler kept the step's loop-invariant operands in vector registers
+// and re-converted them for every slice (5 R2UR + ~9 UMOV / UIADD3 per pair of UTCHMMA, ~115 cycles per MMA measured on the
+// 32-channel layers whose MMAs take 16-32 cycles); here they enter the uniform datapath once per step.
+// fuse2 form, per slice: [a_hi*b_hi | a_hi*b_lo] (idesc2, N = 2*NT, accumulate flag `acc` on the first slice), a_lo*b_hi (idesc).
+__device__ __forceinline__ void umma_step_fuse2(uint32_t d_tmem, uint32_t a_hi, uint32_t img16, uint32_t b_hi, uint32_t idesc2,
+                                                uint32_t idesc, uint32_t acc, uint32_t ks) {
+  asm volatile(
+      "{\n\t.reg .pred pacc, pt, q1, q2, q3;\n\t.reg .b32 a1, a2, b1;\n\t.reg .b64 da, db, dc;\n\t"
+      "setp.ne.b32 pacc, %6, 0;\n\tsetp.eq.u32 pt, %7, %7;\n\t"
+      "setp.gt.u32 q1, %7, 1;\n\tsetp.gt.u32 q2, %7, 2;\n\tsetp.gt.u32 q3, %7, 3;\n\t"
+      "add.u32 a2, %1, %2;\n\t"
+      "mov.b64 da, {%1, %8};\n\tmov.b64 db, {%3, %8};\n\tmov.b64 dc, {a2, %8};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pacc;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], dc, db, %5, pt;\n\t"
+      "add.u32 a1, %1, 2;\n\tadd.u32 b1, %3, 2;\n\tadd.u32 a2, a2, 2;\n\t"
+      "mov.b64 da, {a1, %8};\n\tmov.b64 db, {b1, %8};\n\tmov.b64 dc, {a2, %8};\n\t"
+      "@q1 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+      "@q1 tcgen05.mma.cta_group::1.kind::f16 [%0], dc, db, %5, pt;\n\t"
+      "add.u32 a1, %1, 4;\n\tadd.u32 b1, %3, 4;\n\tadd.u32 a2, a2, 2;\n\t"
+      "mov.b64 da, {a1, %8};\n\tmov.b64 db, {b1, %8};\n\tmov.b64 dc, {a2, %8};\n\t"
+      "@q2 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+      "@q2 tcgen05.mma.cta_group::1.kind::f16 [%0], dc, db, %5, pt;\n\t"
+      "add.u32 a1, %1, 6;\n\tadd.u32 b1, %3, 6;\n\tadd.u32 a2, a2, 2;\n\t"
+      "mov.b64 da, {a1, %8};\n\tmov.b64 db, {b1, %8};\n\tmov.b64 dc, {a2, %8};\n\t"
+      "@q3 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, pt;\n\t"
+      "@q3 tcgen05.mma.cta_group::1.kind::f16 [%0], dc, db, %5, pt;\n\t}"
+      ::"r"(d_tmem), "r"(a_hi), "r"(img16), "r"(b_hi), "r"(idesc2), "r"(idesc), "r"(acc), "r"(ks), "r"(kDescHiSw128)
+      : "memory");
+}
+// plain form, per slice: a_lo*b_hi (accumulate flag `acc` on the first slice), a_hi*b_lo (b_lo = b_hi + bplane16), a_hi*b_hi
+__device__ __forceinline__ void umma_step_x3(uint32_t d_tmem, uint32_t a_hi, uint32_t img16, uint32_t b_hi, uint32_t bplane16, uint32_t idesc,
+                                             uint32_t acc, uint32_t ks) {
+  asm volatile(
+      "{\n\t.reg .pred pacc, pt, q1, q2, q3;\n\t.reg .b32 a1, a2, b1, b2;\n\t.reg .b64 da, db, dc, dd;\n\t"
+      "setp.ne.b32 pacc, %6, 0;\n\tsetp.eq.u32 pt, %7, %7;\n\t"
+      "setp.gt.u32 q1, %7, 1;\n\tsetp.gt.u32 q2, %7, 2;\n\tsetp.gt.u32 q3, %7, 3;\n\t"
+      "add.u32 a2, %1, %2;\n\tadd.u32 b2, %3, %4;\n\t"
+      "mov.b64 da, {%1, %8};\n\tmov.b64 db, {%3, %8};\n\tmov.b64 dc, {a2, %8};\n\tmov.b64 dd, {b2, %8};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], dc, db, %5, pacc;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, dd, %5, pt;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 a1, %1, 2;\n\tadd.u32 b1, %3, 2;\n\tadd.u32 a2, a2, 2;\n\tadd.u32 b2, b2, 2;\n\t"
+      "mov.b64 da, {a1, %8};\n\tmov.b64 db, {b1, %8};\n\tmov.b64 dc, {a2, %8};\n\tmov.b64 dd, {b2, %8};\n\t"
+      "@q1 tcgen05.mma.cta_group::1.kind::f16 [%0], dc, db, %5, pt;\n\t"
+      "@q1 tcgen05.mma.cta_group::1.kind::f16 [%0], da, dd, %5, pt;\n\t"
+      "@q1 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 a1, %1, 4;\n\tadd.u32 b1, %3, 4;\n\tadd.u32 a2, a2, 2;\n\tadd.u32 b2, b2, 2;\n\t"
+      "mov.b64 da, {a1, %8};\n\tmov.b64 db, {b1, %8};\n\tmov.b64 dc, {a2, %8};\n\tmov.b64 dd, {b2, %8};\n\t"
+      "@q2 tcgen05.mma.cta_group::1.kind::f16 [%0], dc, db, %5, pt;\n\t"
+      "@q2 tcgen05.mma.cta_group::1.kind::f16 [%0], da, dd, %5, pt;\n\t"
+      "@q2 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t"
+      "add.u32 a1, %1, 6;\n\tadd.u32 b1, %3, 6;\n\tadd.u32 a2, a2, 2;\n\tadd.u32 b2, b2, 2;\n\t"
+      "mov.b64 da, {a1, %8};\n\tmov.b64 db, {b1, %8};\n\tmov.b64 dc, {a2, %8};\n\tmov.b64 dd, {b2, %8};\n\t"
+      "@q3 tcgen05.mma.cta_group::1.kind::f16 [%0], dc, db, %5, pt;\n\t"
+      "@q3 tcgen05.mma.cta_group::1.kind::f16 [%0], da, dd, %5, pt;\n\t"
+      "@q3 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n\t}"
+      ::"r"(d_tmem), "r"(a_hi), "r"(img16), "r"(b_hi), "r"(bplane16), "r"(idesc), "r"(acc), "r"(ks), "r"(kDescHiSw128)
+      : "memory");
+}
 // all previously issued MMAs of this thread complete -> arrive on the mbarrier (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
