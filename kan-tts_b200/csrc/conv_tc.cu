@@ -898,6 +898,7 @@ static int sm_count() {
 static long long* g_trace = nullptr;   // development aid, not thread-safe: set by kt_debug_set_trace
 static int g_dbg = 0;
 void debug_set_flags(int f) { g_dbg = f; }
+int debug_flags() { return g_dbg; }
 void debug_set_trace(long long* dev_buf) { g_trace = dev_buf; }
 
 static bool tc_env_flag(const char* name) {

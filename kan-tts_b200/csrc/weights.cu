@@ -117,6 +117,8 @@ int weight_prepare(const float* v, const float* g, const float* inv_sigma, int m
   return KT_OK;
 }
 
+int debug_flags();   // 2048: skip the weight-norm backward kernel (ablation)
+
 int weight_grad(const float* dw, const float* v, const float* g, const float* norm, const float* inv_sigma,
                 int mode, int d0, int d1, int k, int transposed, int groups, float* dv, float* dg, int accumulate,
                 const float* dbias_src, float* dbias_dst, int nbias, cudaStream_t st) {
@@ -124,7 +126,7 @@ int weight_grad(const float* dw, const float* v, const float* g, const float* no
   KT_REQUIRE(mode == 0 || (mode == 1 && g && norm && dg), "weight_grad: mode 1 needs g, norm, dg");
   WLayout L{d0, d1, k, transposed, groups};
   KT_REQUIRE((dbias_dst == nullptr) == (dbias_src == nullptr) && nbias >= 0, "weight_grad: dbias_src / dbias_dst must come together");
-  weight_grad_kernel<<<d0, 256, 0, st>>>(dw, v, g, norm, inv_sigma, mode, L, dv, dg, accumulate, dbias_src, dbias_dst, nbias);
+  if (!(debug_flags() & 2048)) weight_grad_kernel<<<d0, 256, 0, st>>>(dw, v, g, norm, inv_sigma, mode, L, dv, dg, accumulate, dbias_src, dbias_dst, nbias);
   KT_CHECK_CUDA(cudaGetLastError());
   return KT_OK;
 }

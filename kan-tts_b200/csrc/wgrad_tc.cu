@@ -563,6 +563,8 @@ struct WgPlan {
   int max_span_q;
 };
 
+int debug_flags();   // conv_tc.cu (kt_debug_set_flags): 256 skip the operand split, 512 skip the MMA kernel, 1024 skip the split-K reduce
+
 static bool wg_want_tma() {
   static const bool on = [] { const char* e = std::getenv("KANTTS_B200_WG_TMA"); return !(e && e[0] == '0'); }();
   return on;
@@ -778,8 +780,10 @@ int conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy,
     __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(ws + pl.planes_b_off);
     const long long na = (long long)p.batch * p.t_a * p.nsub * p.ca, nb = (long long)p.batch * p.t_b * p.nsub * p.cb;
     auto blocks_for = [](long long n8) { return (int)std::max<long long>(1, std::min<long long>((n8 + 255) / 256, 148LL * 16)); };
+    if (!(debug_flags() & 256)) {
     split_planes_kernel<<<blocks_for(na / 8), 256, 0, st>>>(p.a, na / 8, pa, pa + na);
     split_planes_kernel<<<blocks_for(nb / 8), 256, 0, st>>>(p.b, nb / 8, pb, pb + nb);
+    }
     KT_CHECK_CUDA(cudaGetLastError());
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     {
@@ -805,7 +809,7 @@ int conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy,
       cfg_t.store(true, std::memory_order_release);
     }
     dim3 grid(p.groups * p.n_ca_tiles * p.n_cb_tiles, p.ngroups, p.nsplit);
-    wgrad_tma_kernel<<<grid, kWgTmaThreads, pl.smem_tma, st>>>(p, x);
+    if (!(debug_flags() & 512)) wgrad_tma_kernel<<<grid, kWgTmaThreads, pl.smem_tma, st>>>(p, x);
     KT_CHECK_CUDA(cudaGetLastError());
   } else {
   static std::atomic<bool> cfg{false};
@@ -820,8 +824,8 @@ int conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy,
   const long long n = (long long)p.taps_total * p.ca_g0 * p.cb;
   const int blocks = (int)std::max<long long>(1, std::min<long long>((n / 4 + 255) / 256, 148LL * 8));
   const bool fused_bias = dbias != nullptr && p.bias_grp >= 0;
-  if (direct) {
-    // nothing to reduce
+  if (direct || (debug_flags() & 1024)) {
+    // nothing to reduce (or ablation)
   } else if (p.nsplit >= 16) {
     const long long warps = n / 4 + d->c_out;
     const int wblocks = (int)std::max<long long>(1, std::min<long long>((warps + 7) / 8, 148LL * 8));

@@ -8,7 +8,7 @@ import kantts_b200 as K
 from kantts_b200 import ops, train
 
 dev = torch.device("cuda", 0)
-VARIANTS = sys.argv[1:] or ["base", "segments", "no_adam", "no_wgrad", "no_prepare", "no_wgrad_streams"]
+VARIANTS = sys.argv[1:] or ["base", "segments", "no_adam", "no_wgrad", "no_prepare", "no_wgrad_streams", "flags256", "flags512", "flags1024", "flags2048", "flags3840"]
 
 
 def build():
@@ -46,6 +46,8 @@ for var in VARIANTS:
         ops.prepare_weight = prep
     elif var == "no_wgrad_streams":
         ops._WGRAD_ASYNC = False
+    from kantts_b200 import _lib
+    _lib.load().kt_debug_set_flags(int(var[5:]) if var.startswith("flags") else 0)
     step, y, x = build()
     if var == "no_adam":
         step._seg_gopt = lambda: None
