@@ -311,9 +311,17 @@ struct WgTmaExtra {
 };
 
 // fp32 operand -> hi / lo bf16 planes, with the operand's fused transform (pre-activation / activation-derivative mask)
-__global__ void split_planes_kernel(Side s, long long n8, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+// (both operands of a layer in ONE launch: CTAs [0, blocks_a) convert operand A, the rest operand B)
+__global__ void split_planes_kernel(Side sa, long long n8a, __nv_bfloat16* __restrict__ hia, Side sb, long long n8b,
+                                    __nv_bfloat16* __restrict__ hib, int blocks_a) {
+  const bool first = (int)blockIdx.x < blocks_a;
+  const Side s = first ? sa : sb;
+  const long long n8 = first ? n8a : n8b;
+  __nv_bfloat16* hi = first ? hia : hib;
+  __nv_bfloat16* lo = hi + n8 * 8;
+  const long long b0 = first ? blockIdx.x : blockIdx.x - blocks_a, nb = first ? blocks_a : (long long)gridDim.x - blocks_a;
   const bool has_aux = s.mode >= SIDE_DLRELU;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+  for (long long i = b0 * (long long)blockDim.x + threadIdx.x; i < n8; i += nb * blockDim.x) {
     const float4 v0 = __ldg(reinterpret_cast<const float4*>(s.p) + 2 * i), v1 = __ldg(reinterpret_cast<const float4*>(s.p) + 2 * i + 1);
     float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
     if (has_aux) {
@@ -781,8 +789,8 @@ int conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy,
     const long long na = (long long)p.batch * p.t_a * p.nsub * p.ca, nb = (long long)p.batch * p.t_b * p.nsub * p.cb;
     auto blocks_for = [](long long n8) { return (int)std::max<long long>(1, std::min<long long>((n8 + 255) / 256, 148LL * 16)); };
     if (!(debug_flags() & 256)) {
-    split_planes_kernel<<<blocks_for(na / 8), 256, 0, st>>>(p.a, na / 8, pa, pa + na);
-    split_planes_kernel<<<blocks_for(nb / 8), 256, 0, st>>>(p.b, nb / 8, pb, pb + nb);
+      const int ba = blocks_for(na / 8), bb = blocks_for(nb / 8);
+      split_planes_kernel<<<ba + bb, 256, 0, st>>>(p.a, na / 8, pa, p.b, nb / 8, pb, ba);
     }
     KT_CHECK_CUDA(cudaGetLastError());
     const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
