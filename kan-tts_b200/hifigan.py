@@ -146,7 +146,9 @@ class _NormedConv(nn.Module):
 
     def run(self, x, resid=None):
         v, g = self.effective_weight()
-        return ops.conv(x, self.spec, self._cache, v, g, self.bias, resid)
+        if self.norm == "spectral":      # sigma changes with every forward: never part of pair_reuse
+            return ops.conv(x, self.spec, self._cache, v, g, self.bias, resid)
+        return ops.pair_conv(self, x, self.spec, self._cache, v, g, self.bias, resid)
 
     def remove_weight_norm(self):
         if self.norm != "weight":
@@ -724,8 +726,16 @@ class MultiScaleDiscriminator(nn.Module):
 
         def run_scale(d, x):
             if pair_nb is not None and any(getattr(l[0], "norm", "") == "spectral" for l in d.convs):
-                oa, fa = d.forward_rows(x[:pair_nb])
-                ob, fb = d.forward_rows(x[pair_nb:])
+                # the two calls of the reference, in ITS order (the power iteration makes the order observable): the
+                # discriminator phase evaluates the real waveforms first (trainer.py:560-561) -- with pair_state("reuse") the
+                # batch is [re-generated | real], so the second half goes first
+                st = ops._pair_state
+                if st is not None and st[0] == "reuse":
+                    ob, fb = d.forward_rows(x[pair_nb:])
+                    oa, fa = d.forward_rows(x[:pair_nb])
+                else:
+                    oa, fa = d.forward_rows(x[:pair_nb])
+                    ob, fb = d.forward_rows(x[pair_nb:])
                 return (oa, ob), (fa, fb)
             return d.forward_rows(x)
 

@@ -169,11 +169,12 @@ class PreparedWeight:
     """Kernel-layout copies of one layer's effective weight (w_fwd, w_bwd) + the weight-norm
     row norms, valid for one (parameter version) -- see kt_weight_prepare."""
 
-    __slots__ = ("w_fwd", "w_bwd", "norm", "key", "img", "img_stale", "last")
+    __slots__ = ("w_fwd", "w_bwd", "norm", "key", "img", "img_stale", "last", "last_reuse")
 
     def __init__(self):
         self.w_fwd = self.w_bwd = self.norm = None
         self.key = None
+        self.last_reuse = None   # (d, nt_fwd) of the latest pair_reuse forward (a second forward shape per step)
         self.last = None       # (d, nt_fwd, d_bwd, nt_bwd) of the latest forward: what prefetch() re-prepares
         self.img = {}          # (dir, n_tile) -> packed split-bf16 tcgen05 weight tiles
         self.img_stale = set()
@@ -209,6 +210,10 @@ def prefetch_weight(cache, spec, v, g):
         pw.tc_image(spec, d, 0, nt)
     if nt_b and not (_FORCE_FFMA or spec.path == KT_PATH_FFMA):
         pw.tc_image(spec, db, 1, nt_b)
+    if cache.last_reuse is not None and not (_FORCE_FFMA or spec.path == KT_PATH_FFMA):
+        d2, nt2 = cache.last_reuse
+        if nt2:
+            pw.tc_image(spec, d2, 0, nt2)
 
 
 def prepare_weight(cache, spec, v, g):
@@ -458,16 +463,25 @@ class ConvFn(torch.autograd.Function):
     """y = act_out(conv(act_in(x)) + bias) + resid   on channels-last rows."""
 
     @staticmethod
-    def forward(ctx, x, resid, bias, v, g, spec, cache):
+    def forward(ctx, x, resid, bias, v, g, spec, cache, reuse=None):
         lib = _lib.load()
         x = x.contiguous()
         nsub = x.shape[2] if x.dim() == 4 else 1
         B, t_in = x.shape[0], x.shape[1]
         assert x.shape[-1] == spec.c_in, (x.shape, spec)
-        d = spec.desc(B, nsub, t_in)
+        d_full = spec.desc(B, nsub, t_in)
         pw = prepare_weight(cache, spec, v, g)
-        shape = (B, d.t_out, nsub, spec.c_out) if x.dim() == 4 else (B, d.t_out, spec.c_out)
-        y = torch.empty(shape, device=x.device, dtype=torch.float32)
+        shape = (B, d_full.t_out, nsub, spec.c_out) if x.dim() == 4 else (B, d_full.t_out, spec.c_out)
+        if reuse is not None:
+            # pair_reuse: the output of this layer for the batch items [nb_run, B) is already in `y_buf` (same weights, same
+            # inputs, computed earlier in the step); only the first nb_run items are computed, in place
+            y_buf, nb_run = reuse
+            assert tuple(y_buf.shape) == tuple(shape) and y_buf.is_contiguous() and resid is None, (y_buf.shape, shape)
+            y = y_buf.detach()
+            d = spec.desc(nb_run, nsub, t_in)
+        else:
+            y = torch.empty(shape, device=x.device, dtype=torch.float32)
+            d = d_full
         if resid is not None:
             resid = resid.contiguous()
             assert resid.shape == y.shape, (resid.shape, y.shape)
@@ -486,6 +500,7 @@ class ConvFn(torch.autograd.Function):
                                         stream_ptr()), "kt_conv1d_fwd")
         _count(spec.stride if spec.transposed else 1)
         nb = B if _grad_items is None else min(_grad_items, B)     # batch items that carry gradient
+        d = d_full
         db = d if nb == B else spec.desc(nb, nsub, t_in)
         ctx.spec, ctx.d, ctx.nb = spec, db, nb
         ctx.w_bwd, ctx.norm = pw.w_bwd, pw.norm
@@ -503,7 +518,9 @@ class ConvFn(torch.autograd.Function):
         ctx.has_resid, ctx.has_bias, ctx.has_g = resid is not None, bias is not None, g is not None
         ctx.params = (v, g, bias)
         prev = cache.last
-        if nt_b == 0 and prev is not None and prev[3]:     # a no-grad forward keeps the data-gradient plan to prefetch
+        if reuse is not None and prev is not None:
+            cache.last_reuse = (spec.desc(reuse[1], nsub, t_in), nt)   # keep the full-batch shapes for the prefetch, add this one
+        elif nt_b == 0 and prev is not None and prev[3]:   # a no-grad forward keeps the data-gradient plan to prefetch
             cache.last = (d, nt, prev[2], prev[3])
         else:
             cache.last = (d, nt, ctx.d_up or db, nt_b)
@@ -558,11 +575,51 @@ class ConvFn(torch.autograd.Function):
             dres = dy_full.clone()
         dbias, dv, dg = _weight_backward(spec, d, x_, dy, y_, v, g, ctx.params, ctx.norm, ctx.needs_input_grad[3],
                                          ctx.has_g and ctx.needs_input_grad[4], ctx.has_bias and ctx.needs_input_grad[2])
-        return dx, dres, dbias, dv, dg, None, None
+        return dx, dres, dbias, dv, dg, None, None, None
 
 
-def conv(x, spec, cache, v, g=None, bias=None, resid=None):
-    return ConvFn.apply(x, resid, bias, v, g, spec, cache)
+def conv(x, spec, cache, v, g=None, bias=None, resid=None, reuse=None):
+    return ConvFn.apply(x, resid, bias, v, g, spec, cache, reuse)
+
+
+# ---- pair_reuse: one (generated, real) pair batch per phase, the real half computed once per step -----------------------
+# The trainer evaluates every discriminator on the real waveforms twice per step with the SAME weights: in the generator
+# phase (feature-matching targets, trainer.py:527-531) and in the discriminator phase (trainer.py:560).  With
+# pair_state("record") the conv layers of the discriminators keep their pair-batch outputs ([generated | real]); with
+# pair_state("reuse", B) they compute only the first B items (the re-generated waveforms) into those buffers and reuse the
+# real half as is.  Layers whose weights change between two forwards (spectral norm: power iteration) never take part.
+_pair_state = None
+
+
+class pair_state:
+    def __init__(self, mode, nb=None):
+        self.state = None if mode is None else (mode, nb)
+
+    def __enter__(self):
+        global _pair_state
+        self.prev, _pair_state = _pair_state, self.state
+        return self
+
+    def __exit__(self, *exc):
+        global _pair_state
+        _pair_state = self.prev
+        return False
+
+
+def pair_conv(owner, x, spec, cache, v, g, bias, resid=None):
+    """ops.conv for a layer object `owner` that may record / reuse its pair-batch output (see pair_state)."""
+    st = _pair_state
+    if st is None or resid is not None or not x.is_cuda:
+        return conv(x, spec, cache, v, g, bias, resid)
+    mode, nb = st
+    if mode == "record":
+        y = conv(x, spec, cache, v, g, bias)
+        owner._pair_out = y.detach()
+        return y
+    buf = getattr(owner, "_pair_out", None)
+    if buf is None or buf.shape[0] != x.shape[0] or buf.device != x.device:
+        return conv(x, spec, cache, v, g, bias)
+    return conv(x, spec, cache, v, g, bias, None, (buf, nb))
 
 
 # ---- fused ResidualBlock unit (csrc/resblock_tc.cu) -------------------------------------------------------------------

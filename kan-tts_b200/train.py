@@ -60,12 +60,16 @@ class GanStep:
     shape and ``criterion`` as built by the reference's builders (or this package's)."""
 
     def __init__(self, model, optimizer, scheduler, criterion, config, skip_unused_d_grads=True, cuda_graph=False,
-                 graph_warmup=3, pair_discriminators=True):
+                 graph_warmup=3, pair_discriminators=True, reuse_real_half=None):
         self.model, self.optimizer, self.scheduler = model, optimizer, scheduler
         self.criterion, self.config = criterion, config
         self.skip_unused_d_grads = skip_unused_d_grads
         # run each discriminator ONCE per phase on the (generated, real) pair as a batch of 2B (forward_pair)
         self.pair_discriminators = pair_discriminators
+        # the discriminators' forward on the REAL waveforms is the same computation in both phases (same weights, same input):
+        # the generator phase records it, the discriminator phase reuses it (ops.pair_state); spectral-normed scales excluded
+        self.reuse_real_half = (os.environ.get("KANTTS_B200_REUSE_REAL", "1") != "0") if reuse_real_half is None else reuse_real_half
+        self._pair_recorded = False
         self.g_grads = FlatGrads(model["generator"])
         self.d_grads = {k: FlatGrads(m) for k, m in model["discriminator"].items()}
         self.steps = 1
@@ -113,8 +117,9 @@ class GanStep:
                 if paired:
                     # disc(y_) [with grad] and the no_grad disc(y) of trainer.py:527-531 as one batch: only the
                     # first B items (y_) carry gradient, the real half is returned detached
-                    with ops.grad_items(y_.shape[0]):
+                    with ops.grad_items(y_.shape[0]), ops.pair_state("record" if self.reuse_real_half else None):
                         (p_, fmap_), (_, fmap) = disc.forward_pair(y_, y, detach_b=True)
+                    self._pair_recorded = self.reuse_real_half
                     fmap_lst.append(fmap)
                 else:
                     p_, fmap_ = disc(y_)
@@ -160,7 +165,11 @@ class GanStep:
             dis_loss = 0.0
             real_t, fake_t = 0.0, 0.0
             for name, disc in model["discriminator"].items():
-                if self._can_pair():
+                if self._can_pair() and self._pair_recorded:
+                    # [re-generated | real] like the generator phase's batch: the real half is already in the layers' buffers
+                    with ops.pair_state("reuse", y_.shape[0]):
+                        (p_, fmap_), (p, fmap) = disc.forward_pair(y_.detach(), y)
+                elif self._can_pair():
                     (p, fmap), (p_, fmap_) = disc.forward_pair(y, y_.detach())     # trainer.py:560-561 as one batch
                 else:
                     p, fmap = disc(y)
@@ -223,6 +232,7 @@ class GanStep:
 
     def _eager_step(self, y, x):
         self._log = {}
+        self._pair_recorded = False
         if self._g_active():
             self._seg_generator(y, x)
             self.g_grads.all_reduce_mean()

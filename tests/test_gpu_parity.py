@@ -287,6 +287,35 @@ def test_gan_train_step_matches_reference_trainer(golden, force_ffma, pair):
         assert num <= 2e-2 * den, (tag, num, den)      # Adam's first step is lr*sign-like: loose on purpose
 
 
+def test_real_half_reuse_matches_full_recompute(golden):
+    """GanStep(reuse_real_half=True): the discriminator phase computes only the re-generated half of every pair batch and
+    takes the real half from the generator phase's buffers.  Same kernels on the same data per item: losses and parameters
+    must agree with the plain step to rounding (the two steps order the pair batch differently, [fake | real] vs
+    [real | fake], which only permutes the batch-summation order of the weight gradients)."""
+    g = golden("trainstep_small")
+    cfg = _small_config(g)
+    res = {}
+    for reuse in (False, True):
+        torch.manual_seed(0)
+        model, opt, sched = K.hifigan_model_builder(cfg, DEV)
+        model["generator"].load_state_dict(g.group("before/g/"))
+        model["discriminator"]["MultiScaleDiscriminator"].load_state_dict(g.group("before/msd/"))
+        model["discriminator"]["MultiPeriodDiscriminator"].load_state_dict(g.group("before/mpd/"))
+        crit = K.criterion_builder(cfg, DEV)
+        step = K.GanStep(model, opt, sched, crit, cfg, reuse_real_half=reuse)
+        y, x = g.t("y").to(DEV), g.t("x").to(DEV)
+        logs = [K.train.losses_to_float(step.step((y, x))), K.train.losses_to_float(step.step((y.flip(0), x.flip(0))))]
+        mods = {"g": model["generator"], **model["discriminator"]}
+        res[reuse] = (logs, {f"{tag}.{k}": v.detach().clone() for tag, m in mods.items() for k, v in m.state_dict().items()})
+    for la, lb in zip(res[False][0], res[True][0]):
+        for k in la:
+            assert abs(la[k] - lb[k]) <= 1e-4 * max(1.0, abs(la[k])), (k, la[k], lb[k])
+    for k, v in res[False][1].items():
+        w = res[True][1][k]
+        # (Adam turns a sign flip of a ~0 gradient into a 2 * lr difference: loose on purpose, the second step's losses are the check)
+        assert float((v - w).abs().max()) <= 5e-3 * max(1.0, float(v.abs().max())), k
+
+
 @pytest.mark.parametrize("name,cls", [("mpd_small", "MultiPeriodDiscriminator"), ("msd_small", "MultiScaleDiscriminator")])
 def test_forward_pair_equals_two_calls(golden, name, cls):
     """forward_pair(ya, yb) == (d(ya), d(yb)) incl. the spectral-norm power-iteration state, and with
