@@ -25,8 +25,8 @@ for leg in "$@"; do
     diaggan) timeout 900 python scripts/diag_ganstep.py > gpurun_out/diaggan_$TAG.log 2>&1; echo "diaggan rc=$?" >> $S ;;
     benchside) timeout 600 python bench.py --workload c1 --steps 20 --warmup 5 > gpurun_out/bench_c1_$TAG.log 2>&1; echo "bench c1 rc=$?" >> $S
                timeout 900 python bench.py --workload c4 --steps 5 --warmup 3 > gpurun_out/bench_c4_$TAG.log 2>&1; echo "bench c4 rc=$?" >> $S ;;
-    ncu_wgrad) for LN in gen_32_32_k7 mpd_1024_1024_k5_p3; do
-           timeout 600 ncu --set full --clock-control none --import-source on -k regex:wgrad_tc_kernel -s 4 -c 1 -f -o gpurun_out/ncu_wgrad_${LN}_$TAG python scripts/layer_bench.py --only $LN --iters 2 > gpurun_out/ncu_wgrad_$TAG.log 2>&1; echo "ncu_wgrad $LN rc=$?" >> $S; done ;;
+    ncu_wgrad) for LN in ${NCU_WG_LAYERS:-mpd_1024_1024_k5_p3}; do
+           timeout 600 ncu --set full --clock-control none --import-source on -k regex:wgrad_tma_kernel -s 4 -c 1 -f -o gpurun_out/ncu_wgrad_${LN}_$TAG python scripts/layer_bench.py --only $LN --iters 2 > gpurun_out/ncu_wgrad_$TAG.log 2>&1; echo "ncu_wgrad $LN rc=$?" >> $S; done ;;
     ncu_rb) timeout 600 ncu --set full --clock-control none --import-source on -k regex:resblock_tc_kernel -s 2 -c 1 -f -o gpurun_out/ncu_resblock_$TAG env RB_ONLY_BIG=1 python scripts/rb_test.py > gpurun_out/ncu_rb_$TAG.log 2>&1; echo "ncu_rb rc=$?" >> $S ;;
     ablayers) for F in 0 16 32 48 64 80 96 112; do timeout 200 python scripts/layer_bench.py --flags $F --only ${AB_LAYERS:-gen_128_128_k11,mpd_1024_1024_k5_p3,msd_1024_1024_k5,gen_32_32_k7,mpd_128_512_k5s3_p5} >> gpurun_out/ablayers_$TAG.log 2>&1; done; echo "ablayers rc=$?" >> $S ;;
     ncu_layers) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/ncu_layers_$TAG.csv python scripts/layer_bench.py --iters 1 ${NCU_LAYERS:+--only $NCU_LAYERS} > gpurun_out/ncu_layers_$TAG.log 2>&1; echo "ncu_layers rc=$?" >> $S ;;
