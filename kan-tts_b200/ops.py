@@ -617,7 +617,7 @@ def pair_conv(owner, x, spec, cache, v, g, bias, resid=None):
         owner._pair_out = y.detach()
         return y
     buf = getattr(owner, "_pair_out", None)
-    if buf is None or buf.shape[0] != x.shape[0] or buf.device != x.device:
+    if buf is None or buf.shape[0] != x.shape[0] or buf.shape[1] != spec.t_out(x.shape[1]) or buf.device != x.device:
         return conv(x, spec, cache, v, g, bias)
     return conv(x, spec, cache, v, g, bias, None, (buf, nb))
 
