@@ -142,8 +142,11 @@ int kt_conv1d_bwd_data_tc(const KtConv1dDesc* d, const float* dy, const float* y
                           float* dx, void* stream);
 
 /* tcgen05 weight gradient (time is the contraction dimension; split-K partial tiles go to `workspace`,
- * a second kernel reduces them).  kt_conv1d_bwd_weight_tc_workspace: floats of workspace the layer
- * needs, 0 when the layer is not supported (then use kt_conv1d_bwd_weight).  dw / dbias as above. */
+ * a second kernel reduces them -- a single split writes dw / dbias directly).  Plain convs with channel counts % 8 == 0
+ * take the TMA-fed variant: `workspace` then also holds the two operands as hi / lo bf16 planes, written by one
+ * elementwise pre-pass of the call (the planes are 16-byte aligned inside a 256-byte-aligned workspace).
+ * kt_conv1d_bwd_weight_tc_workspace: floats of workspace the layer needs (partials + planes), 0 when the layer is not
+ * supported (then use kt_conv1d_bwd_weight).  dw / dbias as above. */
 int64_t kt_conv1d_bwd_weight_tc_workspace(const KtConv1dDesc* d);
 int kt_conv1d_bwd_weight_tc(const KtConv1dDesc* d, const float* x, const float* dy, const float* y, float* dw,
                             float* dbias, float* workspace, int64_t workspace_floats, void* stream);
