@@ -306,9 +306,15 @@ int kt_resblock_bwd(const KtConv1dDesc* d1, const KtConv1dDesc* d2, const float*
  * clock64() timestamps per role / tile / event into it (int64 [4 roles][16 tiles][4 events]; scripts/tc_trace.py).
  * Process-global and not thread-safe; pass NULL to switch it off (the default). */
 int kt_debug_set_trace(void* dev_buf);
-/* Development aid: ablation switches of the tcgen05 conv kernel's epilogue for timing experiments (bit 0: no residual /
- * mask loads, 1: no global stores, 2: no transposition, 3: no TMEM loads).  RESULTS ARE WRONG while non-zero. */
+/* Development aid: ablation switches for timing experiments.  tcgen05 conv kernel: bit 0 no residual / mask loads, 1 no
+ * global stores, 2 no transposition, 3 no TMEM loads (register epilogue), 4 no weight copies after the first ring pass, 5 no
+ * image staging after the first ring pass, 6 no MMAs; weight-gradient chain: 8 no operand split, 9 no MMA kernel, 10 no
+ * split-K reduce, 11 no weight-norm backward.  RESULTS ARE WRONG while non-zero. */
 int kt_debug_set_flags(int32_t flags);
+/* Test aid (no GPU needed): the plan kt_conv1d_bwd_weight_tc would make for this layer on a GPU box.
+ * out12 = {supported, TMA variant, time steps per chunk, rows per chunk, padded rows, ring stages, shared-memory bytes,
+ * split-K factor, N tile, unit groups, time steps per A box, rows of one A image}. */
+int kt_debug_wgrad_plan(const KtConv1dDesc* d, int32_t* out12);
 
 /* library info */
 const char* kt_last_error(void);

@@ -24,6 +24,7 @@ int conv1d_bwd_weight_tc(const KtConv1dDesc*, const float*, const float*, const 
 int tc_plan(const KtConv1dDesc*, int);
 void debug_set_trace(long long*);
 void debug_set_flags(int);
+void debug_wgrad_plan(const KtConv1dDesc*, int*);
 long long tc_image_bytes(const KtConv1dDesc*, int);
 int tc_pack_layer(const KtConv1dDesc*, int, const float*, void*, cudaStream_t);
 int conv1d_fwd_tc(const KtConv1dDesc*, const float*, const void*, const float*, const float*, float*, cudaStream_t);
@@ -107,6 +108,11 @@ int kt_add3_scale(const float* a, const float* b, const float* c, float scale, f
 }
 int kt_debug_set_trace(void* dev_buf) {
   kt::debug_set_trace(reinterpret_cast<long long*>(dev_buf));
+  return KT_OK;
+}
+int kt_debug_wgrad_plan(const KtConv1dDesc* d, int32_t* out12) {
+  KT_REQUIRE(d && out12, "kt_debug_wgrad_plan: null pointer");
+  kt::debug_wgrad_plan(d, out12);
   return KT_OK;
 }
 int kt_debug_set_flags(int32_t flags) {

@@ -578,7 +578,7 @@ static bool wg_want_tma() {
   return on;
 }
 
-static WgPlan make_plan(const KtConv1dDesc* d, bool allow_tma = true) {
+static WgPlan make_plan(const KtConv1dDesc* d, bool allow_tma = true, bool plan_only = false) {
   WgPlan pl{};
   pl.ok = false;
   WgTcParams& p = pl.p;
@@ -606,7 +606,7 @@ static WgPlan make_plan(const KtConv1dDesc* d, bool allow_tma = true) {
   // transfer) could not hide behind the 1.6 us of MMAs of the other (measured 260 cycles per N = 256 MMA against 77 per
   // N = 128 MMA with three stages, call r2ab).
   const bool tma_ok = allow_tma && !tr && p.up == 1 && (ca % 8) == 0 && (cb % 8) == 0 && (p.ca_g % 8) == 0 && (p.cb_g % 8) == 0 &&
-                      wg_want_tma() && encode_tiled_fn() != nullptr;
+                      (plan_only || (wg_want_tma() && encode_tiled_fn() != nullptr));   // plan_only: host-logic tests without a driver
   p.NT = std::min(tma_ok ? 128 : 256, (p.cb_g + 63) & ~63);
   p.n_cb_tiles = ceil_div(p.cb_g, p.NT);
   p.n_ca_tiles = p.mode == 0 ? ceil_div(p.ca_g, 128) : 1;
@@ -697,7 +697,7 @@ static WgPlan make_plan(const KtConv1dDesc* d, bool allow_tma = true) {
   if (tma_ok) {
     WgTmaExtra& x = pl.x;
     for (int r = 0; r < p.step; ++r)
-      if (p.t_a - r <= 0) return make_plan(d, false);
+      if (p.t_a - r <= 0) return make_plan(d, false, plan_only);
     // tt: the largest chunk (R = tt * nsub <= 128 rows, at most 20 % padding in the last K slice) that still leaves a ring of
     // three stages; else the deepest ring
     int best_tt = 0, best_ns = 0;
@@ -712,7 +712,7 @@ static WgPlan make_plan(const KtConv1dDesc* d, bool allow_tma = true) {
       if (ns > best_ns) { best_ns = ns; best_tt = tt; }
       if (ns >= 3) break;
     }
-    if (best_ns < 2) return make_plan(d, false);
+    if (best_ns < 2) return make_plan(d, false, plan_only);
     x.tt = best_tt; x.R = best_tt * p.nsub; x.Rp = (x.R + 15) & ~15;
     x.a_box_t = best_tt + pl.max_span_q;
     x.rows_a_p = (x.Rp + pl.max_span_q * p.nsub + 7) & ~7;
@@ -749,6 +749,15 @@ static WgPlan make_plan(const KtConv1dDesc* d, bool allow_tma = true) {
     pl.ws_floats = pl.part_floats + fa + fb;
   }
   return pl;
+}
+
+// development / test aid (kt_debug_wgrad_plan): the TMA variant's plan of a layer as it would be made on a GPU box
+// out = {ok, tma, tt, R, Rp, nstages, smem bytes, nsplit, NT, unit groups, a_box_t, rows_a_p}
+void debug_wgrad_plan(const KtConv1dDesc* d, int* out) {
+  const WgPlan pl = make_plan(d, true, true);
+  out[0] = pl.ok; out[1] = pl.tma; out[2] = pl.x.tt; out[3] = pl.x.R; out[4] = pl.x.Rp; out[5] = pl.x.nstages;
+  out[6] = (int)(pl.tma ? pl.smem_tma : pl.smem); out[7] = pl.tma ? pl.nsplit_tma : pl.p.nsplit; out[8] = pl.p.NT; out[9] = pl.p.ngroups;
+  out[10] = pl.x.a_box_t; out[11] = pl.x.rows_a_p;
 }
 
 // floats of workspace needed by conv1d_bwd_weight_tc (0 = layer not supported)

@@ -90,3 +90,46 @@ def test_ffma_path_has_no_tensor_plan(lib):
     _, d = _desc(2, 100, c_in=64, c_out=64, kernel=3, pad_left=2, path=KT_PATH_FFMA)
     spec = ops.ConvSpec(c_in=64, c_out=64, kernel=3, pad_left=2, path=KT_PATH_FFMA)
     assert ops._tc_tile(lib, spec, d, 0) == 0 and ops._wgrad_tc_workspace(lib, spec, d) == 0
+
+
+def test_tma_weight_gradient_plans_respect_the_hardware_limits():
+    """kt_debug_wgrad_plan: the TMA-fed weight-gradient plan (made without a GPU) of the layer shapes of the 24 kHz model and of
+    awkward ones (tiny T, long halos, every period): chunk rows = time steps x sub-sequences padded to whole K = 16 slices, TMA
+    box extents <= 256, >= 2 ring stages inside the 227 KB of shared memory, a positive split-K factor."""
+    import ctypes
+    import numpy as np
+    from kantts_b200 import _lib
+    from kantts_b200._lib import KtConv1dDesc
+    lib = _lib.load()
+
+    def desc(cin, cout, k, stride=1, dil=1, groups=1, batch=16, nsub=1, t_in=2048, pad=None, transposed=0, up=1):
+        pad = (k - 1) * dil // 2 if pad is None else pad
+        t_out = (t_in * up + 2 * pad - dil * (k - 1) - 1) // stride + 1
+        return KtConv1dDesc(batch=batch, nsub=nsub, t_in=t_in, t_out=t_out, c_in=cin, c_out=cout, groups=groups, kernel=k,
+                            stride=stride, dilation=dil, pad_left=pad, transposed=transposed, upsample=up, act_in=0,
+                            act_in_slope=0.0, act_out=1, act_out_slope=0.1, path=0)
+
+    cases = [desc(128, 128, 11), desc(128, 128, 7, dil=3), desc(32, 32, 11, dil=5, t_in=8192), desc(64, 64, 3, t_in=4096),
+             desc(256, 256, 11, t_in=256), desc(80, 512, 7, t_in=32), desc(1024, 1024, 5, batch=32, t_in=33), desc(1024, 1024, 5, t_in=9),
+             desc(128, 256, 41, stride=4, groups=16), desc(1024, 1024, 41, groups=16, t_in=17), desc(512, 1024, 41, stride=4, groups=16, t_in=128),
+             desc(128, 128, 41, stride=4, groups=4, t_in=8192)]
+    for p in (2, 3, 5, 7, 11):
+        cases += [desc(1024, 1024, 5, nsub=p, batch=32, t_in=max(2, 8192 // p // 81)), desc(512, 1024, 5, stride=3, nsub=p, t_in=8192 // p // 27),
+                  desc(128, 512, 5, stride=3, nsub=p, t_in=8192 // p // 9), desc(32, 128, 5, stride=3, nsub=p, t_in=8192 // p // 3)]
+    n_tma = 0
+    for d in cases:
+        out = (ctypes.c_int32 * 12)()
+        assert lib.kt_debug_wgrad_plan(ctypes.byref(d), out) == 0
+        ok, tma, tt, R, Rp, ns, smem, nsplit, NT, ngroups, a_box_t, rows_a_p = list(out)
+        sig = (d.c_in, d.c_out, d.kernel, d.stride, d.groups, d.nsub, d.t_in)
+        assert ok == 1, sig
+        assert nsplit >= 1 and ngroups >= 1 and NT % 64 == 0 and NT <= 256, sig
+        assert smem <= 227 * 1024, (sig, smem)
+        if tma:
+            n_tma += 1
+            assert R == tt * d.nsub and Rp % 16 == 0 and 0 <= Rp - R < 16 and Rp <= 256, (sig, tt, R, Rp)
+            assert 2 <= ns <= 4 and NT <= 128, (sig, ns, NT)
+            assert a_box_t >= tt and a_box_t <= 256 and d.nsub <= 256, (sig, a_box_t)
+            assert rows_a_p % 8 == 0 and rows_a_p >= Rp, (sig, rows_a_p)
+            assert nsplit <= d.batch * -(-d.t_out // tt), sig
+    assert n_tma >= len(cases) - 2     # every channel count here is a multiple of 8: (almost) all take the TMA variant
